@@ -1,0 +1,1088 @@
+// irec_beam.cu -- beam-search coder kernels (sm_100a) behind the C ABI of include/irec.h.
+//
+// Reference path being replaced: rec/coding/beam_search_coder.py:33-151 driven from
+// rec/coding/coder.py:412-491 (GaussianCoder.encode/decode over coder-blocks).
+//
+// Kernels
+//   k_kl_naux              per block KL(q||p) and n_aux                       (coder.py:499-501)
+//   k_beam_encode_resident K1a: one CTA owns one coder-block for all of its partitions: schedule,
+//                          candidate scoring, top-B, beam update all in shared memory / registers
+//   k_beam_decode          K3: replay of the chosen candidates, O(n_aux * D)
+//   k_gp_* / k_topb_merge  K1b/K5: the same step split per partition over the whole grid and over
+//                          candidate ranges (large S, large D, multi-GPU candidate sharding)
+#include "irec_beam.cuh"
+#include "irec_host.h"
+
+// =============================================================================================
+// per-dim schedule of partition t (beam_search_coder.py:64-77,108-109; coder.py:141-154)
+// float32 ops exactly in the reference's order; coefficients of the centred quadratic in float64.
+// =============================================================================================
+struct SchedOut {
+    float sa, A, E, M, cum_next;
+};
+__device__ __forceinline__ SchedOut beam_sched_dim(float cv, float tv, float dmu, float cum, float ratio)
+{
+    SchedOut o;
+    const float v = __fmul_rn(ratio, __fadd_rn(cv, -cum));
+    const float tot = __fadd_rn(v, cum);
+    const float m = __fdiv_rn(__fmul_rn(dmu, tot), cv);
+    const float s2 = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(tot, tot)), __fmul_rn(cv, cv)),
+                               __fdiv_rn(__fmul_rn(tot, __fadd_rn(cv, -tot)), cv));
+    o.sa = __fsqrt_rn(v);
+    o.A = (float)__dmul_rn(0.5, __dsub_rn(__ddiv_rn(1.0, (double)tot), __ddiv_rn(1.0, (double)s2)));
+    o.E = (float)__ddiv_rn((double)m, (double)tot);
+    o.M = m;
+    o.cum_next = __fadd_rn(cum, v);
+    return o;
+}
+
+// per-dim KL term in float64 (TFP kl_normal_normal)
+__device__ __forceinline__ double kl_dim(float tl, float ts, float pl, float ps)
+{
+    const double sp = (double)ps;
+    const double dl = __dsub_rn(log((double)ts), log(sp));
+    const double dm = __dsub_rn(__ddiv_rn((double)tl, sp), __ddiv_rn((double)pl, sp));
+    return __dsub_rn(__dadd_rn(__dmul_rn(0.5, __dmul_rn(dm, dm)), __dmul_rn(0.5, expm1(__dmul_rn(2.0, dl)))), dl);
+}
+
+__device__ __forceinline__ int n_aux_from_kl(float kl, float omega)
+{
+    const float q = __fdiv_rn(kl, omega);
+    if (!(q == q) || isinf(q)) return -1;
+    return (int)ceilf(q);
+}
+
+// canonical tree over nch chunk sums in shared memory (all threads call)
+__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch)
+{
+    const int P = next_pow2_int(nch);
+    __syncthreads();
+    for (int stride = 1; stride < P; stride <<= 1) {
+        for (int i = threadIdx.x * 2 * stride; i + stride < nch; i += blockDim.x * 2 * stride)
+            cs[i] = __dadd_rn(cs[i], cs[i + stride]);
+        __syncthreads();
+    }
+    return cs[0];
+}
+
+// =============================================================================================
+// k_kl_naux
+// =============================================================================================
+#define KL_MAX_CHUNKS 4096
+__global__ void k_kl_naux(const float* __restrict__ t_loc, const float* __restrict__ t_scale,
+                          const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                          const int64_t* __restrict__ gidx, const int64_t* __restrict__ offs, int nb, float omega,
+                          float* out_kl, int32_t* out_n_aux)
+{
+    __shared__ double cs[KL_MAX_CHUNKS];
+    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+        const int64_t off = offs[blk];
+        const int D = (int)(offs[blk + 1] - off);
+        const int nch = (D + 31) >> 5;
+        for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * c + 32);
+            for (int d = 32 * c; d < hi; ++d) {
+                const int64_t gi = gidx ? gidx[off + d] : off + d;
+                acc = __dadd_rn(acc, kl_dim(t_loc[gi], t_scale[gi], p_loc[gi], p_scale[gi]));
+            }
+            cs[c] = acc;
+        }
+        const double kl = block_tree_sum_f64(cs, nch);
+        if (threadIdx.x == 0) {
+            const float klf = (float)kl;
+            if (out_kl) out_kl[blk] = klf;
+            if (out_n_aux) out_n_aux[blk] = n_aux_from_kl(klf, omega);
+        }
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// K3: k_beam_decode  (beam_search_coder.py:124-148)
+// each thread owns quads of dims and replays all partitions for them; no synchronisation needed
+// =============================================================================================
+__global__ void k_beam_decode(const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                              const int64_t* __restrict__ gidx, const int64_t* __restrict__ offs, int nb,
+                              int64_t seed, const int32_t* __restrict__ indices, int max_aux,
+                              const int32_t* __restrict__ n_aux_arr, const float* __restrict__ T,
+                              const float* __restrict__ ratio_tab, float* __restrict__ out)
+{
+    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+        const int64_t off = offs[blk];
+        const int D = (int)(offs[blk + 1] - off);
+        const int n_aux = n_aux_arr[blk];
+        const int32_t* idx = indices + (size_t)blk * max_aux;
+        const int nq = (D + 3) >> 2;
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const int d0 = 4 * q;
+            float ps[4], pl[4], cum[4], smp[4];
+            int64_t gi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = min(d0 + e, D - 1);
+                gi[e] = gidx ? gidx[off + d] : off + d;
+                ps[e] = p_scale[gi[e]]; pl[e] = p_loc[gi[e]];
+                cum[e] = 0.f; smp[e] = 0.f;
+            }
+            int32_t hsum = 0;
+            for (int t = 0; t < n_aux; ++t) {
+                const float ratio = ratio_tab[n_aux - 1 - t];
+                const int32_t s = idx[t];
+                const uint32_t h = (uint32_t)hash_from_sum(hsum);
+                const TfStream st = tf_stream_seeded(seed + t, seed + t);
+                const uint4 u = tf_stream_quad_at(st, (uint64_t)s * (uint64_t)D + (uint64_t)d0);
+                const uint32_t uu[4] = { u.x, u.y, u.z, u.w };
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float cv = __fmul_rn(ps[e], ps[e]);
+                    const float v = __fmul_rn(ratio, __fadd_rn(cv, -cum[e]));
+                    const float a = __fmul_rn(T[beam_mix(beam_r_from_u32(uu[e]), h)], __fsqrt_rn(v));
+                    smp[e] = __fadd_rn(smp[e], a);
+                    cum[e] = __fadd_rn(cum[e], v);
+                }
+                hsum = hsum_extend(hsum, s, t);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (d0 + e < D) out[gi[e]] = __fadd_rn(smp[e], pl[e]);
+        }
+    }
+}
+
+// =============================================================================================
+// K1a: k_beam_encode_resident
+// =============================================================================================
+#define TOPK_CAP 1024
+#define UPD_MAX 8
+
+struct ResidentArgs {
+    const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
+    const int64_t* gidx; const int64_t* offs; int nb;
+    float omega; int S; int B; int64_t seed;
+    int32_t* out_indices; int max_aux; int32_t* out_n_aux; int32_t* out_status; float* out_sample;
+    const float* T; const float* ratio_tab; int ratio_len;
+    int2* hist;            // [gridDim.x][max_aux][BMAX]
+    int* work_counter;     // dynamic block queue
+    int DPmax;             // padded dims capacity of the shared arrays (multiple of 32)
+    int NC;                // capacity of the score array (>= S * BMAX)
+};
+
+template <int BMAX>
+constexpr int resident_max_threads() { return BMAX <= 20 ? 640 : 512; }
+
+template <int BMAX>
+__global__ void __launch_bounds__(resident_max_threads<BMAX>(), 1) k_beam_encode_resident(const ResidentArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int DPm = a.DPmax;
+
+    // ---- shared memory carve-up (all float4-aligned) ----
+    double* s_kl = reinterpret_cast<double*>(smem_raw);                  // [32]
+    float* s_T = reinterpret_cast<float*>(s_kl + 32);                    // [10008]
+    float* s_beams = s_T + 10008;                                        // [BMAX][DPm]
+    float* s_sa = s_beams + (size_t)BMAX * DPm;                          // [DPm] x 8
+    float* s_A = s_sa + DPm; float* s_E = s_A + DPm; float* s_M = s_E + DPm;
+    float* s_cv = s_M + DPm; float* s_tv = s_cv + DPm; float* s_dmu = s_tv + DPm; float* s_cum = s_dmu + DPm;
+    float* s_scores = s_cum + DPm;                                       // [NC]
+    float* s_gmax = s_scores + a.NC;                                     // [1024]
+    float* s_wsc = s_gmax + 1024;                                        // [32] winners' scores
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);             // [32] winners' flat ids
+    int32_t* s_list = s_wid + 32;                                        // [TOPK_CAP]
+    int32_t* s_ctl = s_list + TOPK_CAP;                                  // [4]
+    int32_t* s_hsum = s_ctl + 4;                                         // [2][32]
+    int32_t* s_misc = s_hsum + 64;                                       // [4]: blk, n_aux, status
+
+    for (int i = tid; i < 10007; i += nt) s_T[i] = a.T[i];
+    int2* hist = a.hist + (size_t)blockIdx.x * a.max_aux * BMAX;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_misc[0] = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int blk = s_misc[0];
+        if (blk >= a.nb) break;
+        const int64_t off = a.offs[blk];
+        const int D = (int)(a.offs[blk + 1] - off);
+        const BeamGeom g = make_geom(D);
+
+        // ---- load + KL ----
+        for (int i = tid; i < g.DP; i += nt) {
+            s_cv[i] = 0.f; s_tv[i] = 0.f; s_dmu[i] = 0.f; s_cum[i] = 0.f;
+            s_sa[i] = 0.f; s_A[i] = 0.f; s_E[i] = 0.f; s_M[i] = 0.f;
+        }
+        for (int i = tid; i < BMAX * g.DP; i += nt) s_beams[i] = 0.f;   // rows use stride g.DP
+        __syncthreads();
+        for (int c = tid; c < g.nch; c += nt) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * c + 32);
+            for (int d = 32 * c; d < hi; ++d) {
+                const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
+                acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
+                const int ci = ci_index(d, g.P);
+                s_cv[ci] = __fmul_rn(ps, ps);
+                s_tv[ci] = __fmul_rn(ts, ts);
+                s_dmu[ci] = __fadd_rn(tl, -pl);
+            }
+            s_kl[c] = acc;
+        }
+        const double kld = block_tree_sum_f64(s_kl, g.nch);
+        const int n_aux = n_aux_from_kl((float)kld, a.omega);
+        int status = IREC_BLK_OK;
+        if (n_aux <= 0) status = IREC_BLK_BAD_KL;
+        else if (n_aux > a.max_aux || n_aux > a.ratio_len) status = IREC_BLK_TOO_LONG;
+        if (tid == 0) { a.out_n_aux[blk] = n_aux; a.out_status[blk] = status; }
+        if (status != IREC_BLK_OK) continue;
+
+        if (tid < 64) s_hsum[tid] = 0;
+        int Bcur = 1, hb = 0;                      // hb: which half of s_hsum is current
+        const float4* sa4 = reinterpret_cast<const float4*>(s_sa);
+        const float4* A4 = reinterpret_cast<const float4*>(s_A);
+        const float4* E4 = reinterpret_cast<const float4*>(s_E);
+        const float4* M4 = reinterpret_cast<const float4*>(s_M);
+        const float4* beams4 = reinterpret_cast<const float4*>(s_beams);
+        const int nsg = (a.S + g.SPW - 1) / g.SPW;
+        const int lg = lane & (g.P - 1);
+
+        for (int t = 0; t < n_aux; ++t) {
+            // ---- schedule ----
+            const float ratio = a.ratio_tab[n_aux - 1 - t];
+            for (int i = tid; i < g.DP; i += nt) {
+                const float cv = s_cv[i];
+                if (cv != 0.f) {                   // padding stays zero
+                    const SchedOut o = beam_sched_dim(cv, s_tv[i], s_dmu[i], s_cum[i], ratio);
+                    s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; s_cum[i] = o.cum_next;
+                }
+            }
+            __syncthreads();
+
+            // ---- score all S * Bcur candidates ----
+            const TfStream st = tf_stream_seeded(a.seed + t, a.seed + t);
+            const int32_t* hs = s_hsum + 32 * hb;
+            if (Bcur == 1) {
+                uint32_t h[1] = { (uint32_t)hash_from_sum(hs[0]) };
+                float acc[1];
+                for (int sg = warp; sg < nsg; sg += nwarps) {
+                    const int s = sg * g.SPW + lane / g.P;
+                    score_sample<1, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, 1, acc);
+                    if (lg == 0 && s < a.S) s_scores[s] = (acc[0] == acc[0]) ? acc[0] : __int_as_float(0xff800000);
+                }
+            } else {
+                uint32_t h[BMAX];
+#pragma unroll
+                for (int b = 0; b < BMAX; ++b) h[b] = (uint32_t)hash_from_sum(hs[b]);
+                float acc[BMAX];
+                for (int sg = warp; sg < nsg; sg += nwarps) {
+                    const int s = sg * g.SPW + lane / g.P;
+                    if (Bcur == BMAX)
+                        score_sample<BMAX, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, Bcur, acc);
+                    else
+                        score_sample<BMAX, false, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, Bcur, acc);
+                    if (lg == 0 && s < a.S) {
+#pragma unroll
+                        for (int b = 0; b < BMAX; ++b)
+                            if (b < Bcur)
+                                s_scores[s * Bcur + b] = (acc[b] == acc[b]) ? acc[b] : __int_as_float(0xff800000);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- top-B ----
+            const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+
+            // ---- history + hash sums of the new beams ----
+            int32_t* hs_new = s_hsum + 32 * (hb ^ 1);
+            if (tid < Kout) {
+                const int f = s_wid[tid];
+                const int sj = f / Bcur, bj = f - sj * Bcur;
+                hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
+                hs_new[tid] = hsum_extend(hs[bj], sj, t);
+            }
+
+            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j), in place, two phases ----
+            const int nq = g.DP >> 2;
+            const int Qr = max(1, (nt * UPD_MAX) / Kout);
+            for (int qa = 0; qa < nq; qa += Qr) {
+                const int ntask = min(Qr, nq - qa) * Kout;
+                float4 nv[UPD_MAX];
+#pragma unroll
+                for (int k = 0; k < UPD_MAX; ++k) {
+                    const int task = tid + k * nt;
+                    if (task < ntask) {
+                        const int qq = qa + task / Kout, j = task % Kout;
+                        // physical quad qq -> first dim
+                        const int slot = qq / (8 * g.P), rem = qq - slot * 8 * g.P;
+                        const int iq = rem / g.P, l = rem - iq * g.P;
+                        const int d0 = slot * 32 * g.P + 32 * l + 4 * iq;
+                        const int f = s_wid[j];
+                        const int sj = f / Bcur, bj = f - sj * Bcur;
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (d0 < D) {
+                            const uint32_t h = (uint32_t)hash_from_sum(hs[bj]);
+                            const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                            const float4 sa = sa4[qq];
+                            const float4 ob = beams4[bj * (g.DP >> 2) + qq];
+                            o.x = __fadd_rn(ob.x, __fmul_rn(s_T[beam_mix(beam_r_from_u32(u.x), h)], sa.x));
+                            o.y = __fadd_rn(ob.y, __fmul_rn(s_T[beam_mix(beam_r_from_u32(u.y), h)], sa.y));
+                            o.z = __fadd_rn(ob.z, __fmul_rn(s_T[beam_mix(beam_r_from_u32(u.z), h)], sa.z));
+                            o.w = __fadd_rn(ob.w, __fmul_rn(s_T[beam_mix(beam_r_from_u32(u.w), h)], sa.w));
+                            // dims beyond D inside the last quad: sa = 0 there, so o stays the (zero) padding
+                        }
+                        nv[k] = o;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < UPD_MAX; ++k) {
+                    const int task = tid + k * nt;
+                    if (task < ntask) {
+                        const int qq = qa + task / Kout, j = task % Kout;
+                        reinterpret_cast<float4*>(s_beams)[j * (g.DP >> 2) + qq] = nv[k];
+                    }
+                }
+                __syncthreads();
+            }
+            Bcur = Kout;
+            hb ^= 1;
+        }
+
+        // ---- emit: indices of the best beam (trace the back-pointers) and its sample ----
+        __syncthreads();
+        if (tid == 0) {
+            int j = 0;
+            int32_t* oi = a.out_indices + (size_t)blk * a.max_aux;
+            for (int t = n_aux - 1; t >= 0; --t) {
+                const int2 e = hist[(size_t)t * BMAX + j];
+                oi[t] = e.x;
+                j = e.y;
+            }
+        }
+        for (int d = tid; d < D; d += nt) {
+            const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+            a.out_sample[gi] = __fadd_rn(s_beams[ci_index(d, g.P)], a.p_loc[gi]);
+        }
+    }
+}
+
+// =============================================================================================
+// K1b / K5: general path -- one partition per launch, candidates spread over the grid
+// Device state of one block ("BeamState", owned by the caller, laid out by the library):
+// =============================================================================================
+struct BeamStateHdr {
+    int32_t D, P, nslots, DP;
+    int32_t B, S, max_aux, n_aux;
+    int32_t Bcur, cur;          // cur: which beams/hsum buffer is current
+    int32_t status, pad;
+    float kl, omega;
+    int64_t seed;
+};
+// float arrays after the header (each DP long): cv, tv, dmu, cum, sa, A, E, M, pl(p_loc), beams[2][B][DP]
+// then int32 hsum[2][32], int2 hist[max_aux][32]
+__host__ __device__ inline size_t state_off_floats() { return 256; }
+__host__ __device__ inline float* st_arr(void* state, int which, int DP)
+{
+    return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(state) + state_off_floats()) + (size_t)which * DP;
+}
+__host__ __device__ inline float* st_beams(void* state, int buf, int B, int DP)
+{
+    return st_arr(state, 9, DP) + (size_t)buf * B * DP;
+}
+__host__ __device__ inline int32_t* st_hsum(void* state, int buf, int B, int DP)
+{
+    return reinterpret_cast<int32_t*>(st_arr(state, 9, DP) + (size_t)2 * B * DP) + 32 * buf;
+}
+__host__ __device__ inline int2* st_hist(void* state, int B, int DP)
+{
+    return reinterpret_cast<int2*>(st_hsum(state, 0, B, DP) + 64);
+}
+static size_t state_bytes(int D, int B, int max_aux)
+{
+    const BeamGeom g = make_geom(D);
+    return state_off_floats() + sizeof(float) * ((size_t)9 * g.DP + (size_t)2 * B * g.DP) + sizeof(int32_t) * 64 +
+           sizeof(int2) * (size_t)max_aux * 32 + 64;
+}
+
+// init: gather the block's parameters, KL, n_aux, zero the beams (single CTA)
+__global__ void k_gp_init(void* state, const float* __restrict__ t_loc, const float* __restrict__ t_scale,
+                          const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                          const int64_t* __restrict__ gidx, int64_t off, int D, int B, int S, int max_aux,
+                          int ratio_len, float omega, int64_t seed)
+{
+    __shared__ double cs[KL_MAX_CHUNKS];
+    const BeamGeom g = make_geom(D);
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(state);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    float* cv = st_arr(state, 0, g.DP); float* tv = st_arr(state, 1, g.DP); float* dmu = st_arr(state, 2, g.DP);
+    float* plc = st_arr(state, 8, g.DP);
+    for (int i = tid; i < 9 * g.DP; i += nt) st_arr(state, 0, g.DP)[i] = 0.f;
+    for (int i = tid; i < 2 * B * g.DP; i += nt) st_beams(state, 0, B, g.DP)[i] = 0.f;
+    if (tid < 64) st_hsum(state, 0, B, g.DP)[tid] = 0;
+    __syncthreads();
+    for (int c = tid; c < g.nch; c += nt) {
+        double acc = 0.0;
+        const int hi = min(D, 32 * c + 32);
+        for (int d = 32 * c; d < hi; ++d) {
+            const int64_t gi = gidx ? gidx[off + d] : off + d;
+            const float tl = t_loc[gi], ts = t_scale[gi], pl = p_loc[gi], ps = p_scale[gi];
+            acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
+            const int ci = ci_index(d, g.P);
+            cv[ci] = __fmul_rn(ps, ps); tv[ci] = __fmul_rn(ts, ts); dmu[ci] = __fadd_rn(tl, -pl); plc[ci] = pl;
+        }
+        cs[c] = acc;
+    }
+    const double kld = block_tree_sum_f64(cs, g.nch);
+    if (tid == 0) {
+        const int n_aux = n_aux_from_kl((float)kld, omega);
+        hdr->D = D; hdr->P = g.P; hdr->nslots = g.nslots; hdr->DP = g.DP;
+        hdr->B = B; hdr->S = S; hdr->max_aux = max_aux; hdr->n_aux = n_aux;
+        hdr->Bcur = 1; hdr->cur = 0;
+        hdr->status = n_aux <= 0 ? IREC_BLK_BAD_KL : ((n_aux > max_aux || n_aux > ratio_len) ? IREC_BLK_TOO_LONG : IREC_BLK_OK);
+        hdr->kl = (float)kld; hdr->omega = omega; hdr->seed = seed;
+    }
+}
+
+// schedule of partition t
+__global__ void k_gp_params(void* state, int t, const float* __restrict__ ratio_tab)
+{
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(state);
+    if (hdr->status != IREC_BLK_OK || t >= hdr->n_aux) return;
+    const int DP = hdr->DP;
+    const float ratio = ratio_tab[hdr->n_aux - 1 - t];
+    const float* cv = st_arr(state, 0, DP); const float* tv = st_arr(state, 1, DP); const float* dmu = st_arr(state, 2, DP);
+    float* cum = st_arr(state, 3, DP); float* sa = st_arr(state, 4, DP); float* A = st_arr(state, 5, DP);
+    float* E = st_arr(state, 6, DP); float* M = st_arr(state, 7, DP);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DP; i += gridDim.x * blockDim.x) {
+        const float c = cv[i];
+        if (c != 0.f) {
+            const SchedOut o = beam_sched_dim(c, tv[i], dmu[i], cum[i], ratio);
+            sa[i] = o.sa; A[i] = o.A; E[i] = o.E; M[i] = o.M; cum[i] = o.cum_next;
+        }
+    }
+}
+
+// score candidates s in [s_begin, s_end) x beams, keep the CTA's best B, write them to
+// out_rec[blockIdx.x * B ...] (+ count).  Dynamic smem: T + candidate buffer + top-k scratch.
+struct ScoreArgs {
+    void* state; int t; const float* T;
+    int64_t s_begin, s_end;
+    irec_record_t* out_rec; int32_t* out_cnt;
+    int cand_cap;           // capacity of the per-CTA candidate buffer (>= nwarps*SPW*BMAX + 32)
+};
+
+template <int BMAX>
+__global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(a.state);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (hdr->status != IREC_BLK_OK || a.t >= hdr->n_aux) {
+        if (tid == 0) a.out_cnt[blockIdx.x] = 0;
+        return;
+    }
+    BeamGeom g;
+    g.D = hdr->D; g.P = hdr->P; g.nslots = hdr->nslots; g.DP = hdr->DP; g.nch = (g.D + 31) >> 5; g.SPW = 32 / g.P;
+    const int B = hdr->B, Bcur = hdr->Bcur, cur = hdr->cur;
+    const int cap = a.cand_cap;
+
+    float* s_T = reinterpret_cast<float*>(smem_raw);                 // [10008]
+    float* s_csc = s_T + 10008;                                      // [cap]
+    int32_t* s_cid = reinterpret_cast<int32_t*>(s_csc + cap);        // [cap]
+    float* s_gmax = reinterpret_cast<float*>(s_cid + cap);           // [256]
+    float* s_wsc = s_gmax + 256;                                     // [32]
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);         // [32]
+    int32_t* s_list = s_wid + 32;                                    // [TOPK_CAP]
+    int32_t* s_ctl = s_list + TOPK_CAP;                              // [4]
+    int32_t* s_cnt = s_ctl + 4;                                      // [1] candidate count
+    float* s_tau = reinterpret_cast<float*>(s_cnt + 1);              // [1]
+
+    for (int i = tid; i < 10007; i += nt) s_T[i] = a.T[i];
+    if (tid == 0) { *s_cnt = 0; *s_tau = __int_as_float(0xff800000); }
+
+    const float4* sa4 = reinterpret_cast<const float4*>(st_arr(a.state, 4, g.DP));
+    const float4* A4 = reinterpret_cast<const float4*>(st_arr(a.state, 5, g.DP));
+    const float4* E4 = reinterpret_cast<const float4*>(st_arr(a.state, 6, g.DP));
+    const float4* M4 = reinterpret_cast<const float4*>(st_arr(a.state, 7, g.DP));
+    const float4* beams4 = reinterpret_cast<const float4*>(st_beams(a.state, cur, B, g.DP));
+    const int32_t* hs = st_hsum(a.state, cur, B, g.DP);
+    const TfStream st = tf_stream_seeded(hdr->seed + a.t, hdr->seed + a.t);
+    const int lg = lane & (g.P - 1);
+
+    uint32_t h[BMAX];
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) h[b] = (uint32_t)hash_from_sum(b < Bcur ? hs[b] : 0);
+
+    // contiguous range of sample groups per CTA
+    const int64_t nsg = (a.s_end - a.s_begin + g.SPW - 1) / g.SPW;
+    const int64_t per = (nsg + gridDim.x - 1) / gridDim.x;
+    const int64_t sg0 = (int64_t)blockIdx.x * per, sg1 = min(nsg, sg0 + per);
+    __syncthreads();
+
+    for (int64_t base = sg0; base < sg1; base += nwarps) {
+        const int64_t sg = base + warp;
+        const int64_t s = a.s_begin + sg * g.SPW + lane / g.P;
+        const bool valid = sg < sg1 && s < a.s_end;
+        const uint64_t s_eff = (uint64_t)(valid ? s : a.s_begin);
+        float acc[BMAX];
+        if (g.nslots > 1)
+            score_sample<BMAX, false, true>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
+        else if (Bcur == BMAX)
+            score_sample<BMAX, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
+        else
+            score_sample<BMAX, false, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
+        const float tau = *s_tau;
+        if (valid && lg == 0) {
+#pragma unroll
+            for (int b = 0; b < BMAX; ++b) {
+                if (b < Bcur) {
+                    const float v = (acc[b] == acc[b]) ? acc[b] : __int_as_float(0xff800000);
+                    if (v >= tau) {
+                        const int pos = atomicAdd(s_cnt, 1);
+                        s_csc[pos] = v;
+                        s_cid[pos] = (int32_t)(s * Bcur + b);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int cnt = *s_cnt;
+        if (cnt > B) {
+            const int Kout = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+            if (tid < Kout) { s_csc[tid] = s_wsc[tid]; s_cid[tid] = s_wid[tid]; }
+            if (tid == 0) { *s_cnt = Kout; if (Kout == B) *s_tau = s_wsc[Kout - 1]; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // final ordering of whatever is left (<= B entries, possibly unsorted if never compacted)
+    const int cnt = *s_cnt;
+    const int Kout = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+    if (tid < Kout) {
+        irec_record_t r;
+        const int f = s_wid[tid];
+        r.score = s_wsc[tid]; r.s = f / Bcur; r.b = f - r.s * Bcur; r.pad = 0;
+        a.out_rec[(size_t)blockIdx.x * B + tid] = r;
+    }
+    if (tid == 0) a.out_cnt[blockIdx.x] = Kout;
+}
+
+// merge: records laid out as n_lists lists of stride `stride`, list i has cnt[i] valid entries
+// (cnt == nullptr: every list is full with `stride` entries... use n_valid).  Output best B, sorted.
+__global__ void __launch_bounds__(256) k_topb_merge(const irec_record_t* __restrict__ rec, const int32_t* __restrict__ cnt,
+                                                    int n_lists, int stride, const int32_t* __restrict__ bcur_ptr, int bcur_val,
+                                                    int B, irec_record_t* out_rec, int32_t* out_cnt, float* g_sc, int32_t* g_id)
+{
+    const int Bcur = bcur_ptr ? *bcur_ptr : bcur_val;
+    __shared__ float s_gmax[256];
+    __shared__ float s_wsc[32];
+    __shared__ int32_t s_wid[32];
+    __shared__ int32_t s_list[TOPK_CAP];
+    __shared__ int32_t s_ctl[4];
+    __shared__ int32_t s_n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // compact valid records into (g_sc, g_id) -- order is irrelevant for the result
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i = tid; i < n_lists * stride; i += nt) {
+        const int li = i / stride, e = i - li * stride;
+        const int c = cnt ? cnt[li] : stride;
+        if (e < c) {
+            const int pos = atomicAdd(&s_n, 1);
+            g_sc[pos] = rec[i].score;
+            g_id[pos] = rec[i].s * Bcur + rec[i].b;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    const int Kout = block_topk(g_sc, g_id, n, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+    if (tid < Kout) {
+        irec_record_t r;
+        const int f = s_wid[tid];
+        r.score = s_wsc[tid]; r.s = f / Bcur; r.b = f - r.s * Bcur; r.pad = 0;
+        out_rec[tid] = r;
+    }
+    if (tid == 0) *out_cnt = Kout;
+}
+
+// commit: winners -> new beams (other buffer), hash sums, history; flips the state
+__global__ void k_gp_commit(void* state, int t, const irec_record_t* __restrict__ win, const int32_t* __restrict__ n_win,
+                            const float* __restrict__ T)
+{
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(state);
+    if (hdr->status != IREC_BLK_OK || t >= hdr->n_aux) return;
+    const int D = hdr->D, P = hdr->P, DP = hdr->DP, B = hdr->B, cur = hdr->cur;
+    const int K = *n_win;
+    const float4* sa4 = reinterpret_cast<const float4*>(st_arr(state, 4, DP));
+    const float4* old4 = reinterpret_cast<const float4*>(st_beams(state, cur, B, DP));
+    float4* new4 = reinterpret_cast<float4*>(st_beams(state, cur ^ 1, B, DP));
+    const int32_t* hs = st_hsum(state, cur, B, DP);
+    int32_t* hs_new = st_hsum(state, cur ^ 1, B, DP);
+    int2* hist = st_hist(state, B, DP);
+    const TfStream st = tf_stream_seeded(hdr->seed + t, hdr->seed + t);
+    const int nq = DP >> 2;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int task = gtid; task < nq * K; task += gridDim.x * blockDim.x) {
+        const int qq = task / K, j = task - qq * K;
+        const int slot = qq / (8 * P), rem = qq - slot * 8 * P;
+        const int iq = rem / P, l = rem - iq * P;
+        const int d0 = slot * 32 * P + 32 * l + 4 * iq;
+        const int sj = win[j].s, bj = win[j].b;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d0 < D) {
+            const uint32_t h = (uint32_t)hash_from_sum(hs[bj]);
+            const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+            const float4 sa = sa4[qq];
+            const float4 ob = old4[bj * nq + qq];
+            o.x = __fadd_rn(ob.x, __fmul_rn(T[beam_mix(beam_r_from_u32(u.x), h)], sa.x));
+            o.y = __fadd_rn(ob.y, __fmul_rn(T[beam_mix(beam_r_from_u32(u.y), h)], sa.y));
+            o.z = __fadd_rn(ob.z, __fmul_rn(T[beam_mix(beam_r_from_u32(u.z), h)], sa.z));
+            o.w = __fadd_rn(ob.w, __fmul_rn(T[beam_mix(beam_r_from_u32(u.w), h)], sa.w));
+        }
+        new4[j * nq + qq] = o;
+    }
+    if (gtid < K) {
+        hist[(size_t)t * 32 + gtid] = make_int2(win[gtid].s, win[gtid].b);
+        hs_new[gtid] = hsum_extend(hs[win[gtid].b], win[gtid].s, t);
+    }
+}
+// flips cur / Bcur after commit (separate tiny launch so that every CTA of k_gp_commit saw the old header)
+__global__ void k_gp_flip(void* state, int t, const int32_t* __restrict__ n_win)
+{
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(state);
+    if (hdr->status != IREC_BLK_OK || t >= hdr->n_aux) return;
+    hdr->cur ^= 1;
+    hdr->Bcur = *n_win;
+}
+
+// finish: indices (back-pointer trace) + sample of the best beam
+__global__ void k_gp_finish(void* state, const int64_t* __restrict__ gidx, int64_t off, int32_t* out_indices,
+                            int32_t* out_n_aux, int32_t* out_status, float* out_sample)
+{
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(state);
+    const int D = hdr->D, P = hdr->P, DP = hdr->DP, B = hdr->B;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (out_n_aux) *out_n_aux = hdr->n_aux;
+        if (out_status) *out_status = hdr->status;
+        if (hdr->status == IREC_BLK_OK) {
+            const int2* hist = st_hist(state, B, DP);
+            int j = 0;
+            for (int t = hdr->n_aux - 1; t >= 0; --t) {
+                const int2 e = hist[(size_t)t * 32 + j];
+                out_indices[t] = e.x;
+                j = e.y;
+            }
+        }
+    }
+    if (hdr->status != IREC_BLK_OK) return;
+    const float* beam0 = st_beams(state, hdr->cur, B, DP);
+    const float* plc = st_arr(state, 8, DP);
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+        const int64_t gi = gidx ? gidx[off + d] : off + d;
+        const int ci = ci_index(d, P);
+        out_sample[gi] = __fadd_rn(beam0[ci], plc[ci]);
+    }
+}
+
+// raw stream (tests)
+__global__ void k_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out)
+{
+    const TfStream st = tf_stream_seeded(q, q);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = (uint64_t)(start + i);
+        const uint4 u = tf_stream_group(st, j >> 2);
+        const uint32_t v[4] = { u.x, u.y, u.z, u.w };
+        out[i] = (int32_t)beam_r_from_u32(v[j & 3]);
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+template <int BMAX>
+static size_t resident_smem_bytes(int DPmax, int NC)
+{
+    size_t fl = 10008 + (size_t)BMAX * DPmax + (size_t)8 * DPmax + NC + 1024 + 32;
+    size_t in = 32 + TOPK_CAP + 4 + 64 + 4;
+    return 32 * sizeof(double) + fl * sizeof(float) + in * sizeof(int32_t) + 16;
+}
+
+static int pick_bmax(int B)
+{
+    const int opts[] = { 1, 2, 4, 8, 10, 16, 20, 32 };
+    for (int o : opts) if (B <= o) return o;
+    return -1;
+}
+
+struct ResidentPlan {
+    bool ok; int bmax; int nthreads; size_t smem; int DPmax; int NC; int grid;
+};
+
+template <int BMAX>
+static ResidentPlan plan_resident_t(int nb, int max_D, int S, int B)
+{
+    ResidentPlan p{};
+    p.ok = false; p.bmax = BMAX;
+    if (max_D > 1024 || (int64_t)S * BMAX > 32768) return p;
+    const BeamGeom g = make_geom(max_D);
+    p.DPmax = g.DP;
+    p.NC = ((S * BMAX + 31) / 32) * 32;
+    p.smem = resident_smem_bytes<BMAX>(p.DPmax, p.NC);
+    const IrecDevice& dev = irec_device();
+    if (p.smem > (size_t)dev.max_smem_optin) return p;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_beam_encode_resident<BMAX>) != cudaSuccess) return p;
+    int max_threads = (65536 / (fa.numRegs > 0 ? fa.numRegs : 64)) / 32 * 32;
+    if (max_threads > fa.maxThreadsPerBlock) max_threads = fa.maxThreadsPerBlock / 32 * 32;
+    if (max_threads > 1024) max_threads = 1024;
+    if (max_threads < 64) return p;
+    // one sample group per warp and round; pick the warp count that balances the rounds
+    const int nsg = (S + g.SPW - 1) / g.SPW;
+    const int maxw = max_threads / 32;
+    const int rounds = (nsg + maxw - 1) / maxw;
+    int nw = (nsg + rounds - 1) / rounds;
+    if (nw < 8) nw = std::min(8, maxw);           // keep enough threads for the elementwise phases
+    p.nthreads = nw * 32;
+    if (cudaFuncSetAttribute(k_beam_encode_resident<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+        return p;
+    p.grid = std::min(nb, dev.sm_count);
+    p.ok = true;
+    return p;
+}
+
+static ResidentPlan plan_resident(int nb, int max_D, int S, int B)
+{
+    switch (pick_bmax(B)) {
+        case 1: return plan_resident_t<1>(nb, max_D, S, B);
+        case 2: return plan_resident_t<2>(nb, max_D, S, B);
+        case 4: return plan_resident_t<4>(nb, max_D, S, B);
+        case 8: return plan_resident_t<8>(nb, max_D, S, B);
+        case 10: return plan_resident_t<10>(nb, max_D, S, B);
+        case 16: return plan_resident_t<16>(nb, max_D, S, B);
+        case 20: return plan_resident_t<20>(nb, max_D, S, B);
+        case 32: return plan_resident_t<32>(nb, max_D, S, B);
+    }
+    ResidentPlan p{}; p.ok = false; return p;
+}
+
+template <int BMAX>
+static void launch_resident_t(const ResidentPlan& p, const ResidentArgs& a, cudaStream_t s)
+{
+    k_beam_encode_resident<BMAX><<<p.grid, p.nthreads, p.smem, s>>>(a);
+    irec_count_launch();
+}
+static void launch_resident(const ResidentPlan& p, const ResidentArgs& a, cudaStream_t s)
+{
+    switch (p.bmax) {
+        case 1: launch_resident_t<1>(p, a, s); break;
+        case 2: launch_resident_t<2>(p, a, s); break;
+        case 4: launch_resident_t<4>(p, a, s); break;
+        case 8: launch_resident_t<8>(p, a, s); break;
+        case 10: launch_resident_t<10>(p, a, s); break;
+        case 16: launch_resident_t<16>(p, a, s); break;
+        case 20: launch_resident_t<20>(p, a, s); break;
+        case 32: launch_resident_t<32>(p, a, s); break;
+    }
+}
+
+// ---- general path helpers ----
+#define GP_THREADS 256
+static size_t gp_score_smem(int cand_cap)
+{
+    return sizeof(float) * (10008 + (size_t)cand_cap + 256 + 32) + sizeof(int32_t) * ((size_t)cand_cap + 32 + TOPK_CAP + 4 + 2) + 16;
+}
+static int gp_cand_cap(int D, int bmax)
+{
+    const BeamGeom g = make_geom(D);
+    return (GP_THREADS / 32) * g.SPW * bmax + 64;
+}
+static int gp_score_grid(int D, int64_t n_samples)
+{
+    const BeamGeom g = make_geom(D);
+    const int64_t nsg = (n_samples + g.SPW - 1) / g.SPW;
+    const int64_t per_cta_min = (GP_THREADS / 32);           // at least one round of work per CTA
+    int64_t grid = (nsg + per_cta_min - 1) / per_cta_min;
+    const int cap = irec_device().sm_count * 4;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return (int)grid;
+}
+
+template <int BMAX>
+static int launch_gp_score_t(const ScoreArgs& a, int grid, size_t smem, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(k_gp_score_topb<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)irec_device().max_smem_optin) != cudaSuccess)
+            return IREC_E_CUDA;
+        attr_done = true;
+    }
+    k_gp_score_topb<BMAX><<<grid, GP_THREADS, smem, s>>>(a);
+    irec_count_launch();
+    return IREC_OK;
+}
+static int launch_gp_score(int bmax, const ScoreArgs& a, int grid, size_t smem, cudaStream_t s)
+{
+    switch (bmax) {
+        case 1: return launch_gp_score_t<1>(a, grid, smem, s);
+        case 2: return launch_gp_score_t<2>(a, grid, smem, s);
+        case 4: return launch_gp_score_t<4>(a, grid, smem, s);
+        case 8: return launch_gp_score_t<8>(a, grid, smem, s);
+        case 10: return launch_gp_score_t<10>(a, grid, smem, s);
+        case 16: return launch_gp_score_t<16>(a, grid, smem, s);
+        case 20: return launch_gp_score_t<20>(a, grid, smem, s);
+        case 32: return launch_gp_score_t<32>(a, grid, smem, s);
+    }
+    return IREC_E_INVALID;
+}
+
+extern "C" {
+
+int irec_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (n <= 0) return IREC_OK;
+    k_beam_uniform_int<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(q, start, n, out);
+    irec_count_launch();
+    return irec_check_launch("k_beam_uniform_int");
+}
+
+int irec_kl_naux(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                 const int64_t* gather_idx, const int64_t* block_offsets, int nb, float omega,
+                 float* out_kl, int32_t* out_n_aux, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (nb <= 0) return IREC_OK;
+    k_kl_naux<<<std::min(nb, 4 * irec_device().sm_count), 256, 0, (cudaStream_t)stream>>>(
+        t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, out_kl, out_n_aux);
+    irec_count_launch();
+    return irec_check_launch("k_kl_naux");
+}
+
+int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
+                     const int64_t* block_offsets, int nb, int S, int64_t seed,
+                     const int32_t* indices, int max_aux, const int32_t* n_aux,
+                     float* out_sample, void* stream)
+{
+    IREC_ENSURE_INIT();
+    (void)S;
+    if (nb <= 0) return IREC_OK;
+    k_beam_decode<<<std::min(nb, 8 * irec_device().sm_count), 256, 0, (cudaStream_t)stream>>>(
+        p_loc, p_scale, gather_idx, block_offsets, nb, seed, indices, max_aux, n_aux, irec_device().d_T,
+        irec_device().d_ratio, out_sample);
+    irec_count_launch();
+    return irec_check_launch("k_beam_decode");
+}
+
+// ---------------- opaque per-block state API (general path; multi-GPU candidate sharding) ------
+size_t irec_beam_state_bytes(int D, int B, int max_aux) { return state_bytes(D, B, max_aux); }
+
+int irec_beam_state_init(void* state, const float* t_loc, const float* t_scale, const float* p_loc,
+                         const float* p_scale, const int64_t* gather_idx, int64_t offset, int D, float omega, int S,
+                         int B, int max_aux, int64_t seed, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (D <= 0 || B <= 0 || B > 32 || S <= 0 || max_aux <= 0) return irec_fail(IREC_E_INVALID, "beam_state_init: bad sizes");
+    if (((D + 31) >> 5) > KL_MAX_CHUNKS) return irec_fail(IREC_E_CAPACITY, "beam_state_init: D too large (max 131072 per block)");
+    if ((int64_t)S * B >= (1LL << 31)) return irec_fail(IREC_E_CAPACITY, "beam_state_init: S*B must be < 2^31");
+    k_gp_init<<<1, 256, 0, (cudaStream_t)stream>>>(state, t_loc, t_scale, p_loc, p_scale, gather_idx, offset, D, B, S,
+                                                   max_aux, irec_device().ratio_len, omega, seed);
+    irec_count_launch();
+    return irec_check_launch("k_gp_init");
+}
+
+/* reads n_aux/status/kl back (synchronises the stream) */
+int irec_beam_state_query(const void* state, int32_t* n_aux, int32_t* status, float* kl, void* stream)
+{
+    BeamStateHdr h;
+    if (cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+        return irec_fail(IREC_E_CUDA, "beam_state_query: copy failed");
+    if (n_aux) *n_aux = h.n_aux;
+    if (status) *status = h.status;
+    if (kl) *kl = h.kl;
+    return IREC_OK;
+}
+
+size_t irec_beam_step_workspace_bytes(int D, int B)
+{
+    const int grid_max = irec_device().sm_count * 4;
+    return sizeof(irec_record_t) * ((size_t)grid_max * 32 + 32) + sizeof(int32_t) * ((size_t)grid_max + 8) +
+           (sizeof(float) + sizeof(int32_t)) * ((size_t)grid_max * 32 + 64) + 256;
+}
+
+/* schedule of partition t + local top-B over candidates [s_begin, s_end):
+ * out_records [B] (sorted best first), out_count [1] */
+int irec_beam_step_score(void* state, int D, int B, int t, int64_t s_begin, int64_t s_end, int do_params,
+                         irec_record_t* out_records, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                         void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    const int bmax = pick_bmax(B);
+    if (bmax < 0) return irec_fail(IREC_E_INVALID, "beam_step_score: n_beams must be <= 32");
+    if (workspace_bytes < irec_beam_step_workspace_bytes(D, B)) return irec_fail(IREC_E_CAPACITY, "beam_step_score: workspace too small");
+    const BeamGeom g = make_geom(D);
+    if (do_params) {
+        k_gp_params<<<std::max(1, std::min((g.DP + 255) / 256, 64)), 256, 0, s>>>(state, t, irec_device().d_ratio);
+        irec_count_launch();
+    }
+    const int grid_max = irec_device().sm_count * 4;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    irec_record_t* rec = reinterpret_cast<irec_record_t*>(w);
+    int32_t* cnt = reinterpret_cast<int32_t*>(rec + (size_t)grid_max * 32 + 32);
+    float* g_sc = reinterpret_cast<float*>(cnt + grid_max + 8);
+    int32_t* g_id = reinterpret_cast<int32_t*>(g_sc + (size_t)grid_max * 32 + 64);
+
+    const int64_t ns = s_end > s_begin ? s_end - s_begin : 0;
+    const int grid = gp_score_grid(D, ns);
+    const int cap = gp_cand_cap(D, bmax);
+    ScoreArgs a;
+    a.state = state; a.t = t; a.T = irec_device().d_T; a.s_begin = s_begin; a.s_end = s_end;
+    a.out_rec = rec; a.out_cnt = cnt; a.cand_cap = cap;
+    int rc = launch_gp_score(bmax, a, grid, gp_score_smem(cap), s);
+    if (rc != IREC_OK) return irec_fail(rc, "beam_step_score: launch failed");
+    // Bcur is only known on the device: the merge kernel reads ids as s*Bcur+b with the header's Bcur
+    k_topb_merge<<<1, 256, 0, s>>>(rec, cnt, grid, B, &reinterpret_cast<BeamStateHdr*>(state)->Bcur, 0, B, out_records,
+                                   out_count, g_sc, g_id);
+    irec_count_launch();
+    return irec_check_launch("beam_step_score");
+}
+
+/* merge n_lists x B gathered records (counts[i] valid in list i; counts may be NULL = all B valid)
+ * and commit the winners: new beams, hash sums, history; advances the state to partition t+1 */
+int irec_beam_step_commit(void* state, int D, int B, int t, const irec_record_t* records, const int32_t* counts,
+                          int n_lists, void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (workspace_bytes < irec_beam_step_workspace_bytes(D, B)) return irec_fail(IREC_E_CAPACITY, "beam_step_commit: workspace too small");
+    if (n_lists > irec_device().sm_count * 4) return irec_fail(IREC_E_CAPACITY, "beam_step_commit: too many lists");
+    const int grid_max = irec_device().sm_count * 4;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    irec_record_t* rec = reinterpret_cast<irec_record_t*>(w);
+    int32_t* cnt = reinterpret_cast<int32_t*>(rec + (size_t)grid_max * 32 + 32);
+    float* g_sc = reinterpret_cast<float*>(cnt + grid_max + 8);
+    int32_t* g_id = reinterpret_cast<int32_t*>(g_sc + (size_t)grid_max * 32 + 64);
+    irec_record_t* win = rec + (size_t)grid_max * 32;       // last 32 records of the workspace
+    int32_t* nwin = cnt + grid_max;
+    k_topb_merge<<<1, 256, 0, s>>>(records, counts, n_lists, B, &reinterpret_cast<BeamStateHdr*>(state)->Bcur, 0, B, win, nwin,
+                                   g_sc, g_id);
+    irec_count_launch();
+    const BeamGeom g = make_geom(D);
+    const int tasks = (g.DP >> 2) * B;
+    k_gp_commit<<<std::max(1, std::min((tasks + 255) / 256, irec_device().sm_count * 2)), 256, 0, s>>>(
+        state, t, win, nwin, irec_device().d_T);
+    irec_count_launch();
+    k_gp_flip<<<1, 1, 0, s>>>(state, t, nwin);
+    irec_count_launch();
+    return irec_check_launch("beam_step_commit");
+}
+
+int irec_beam_state_finish(void* state, int D, const int64_t* gather_idx, int64_t offset, int32_t* out_indices,
+                           int32_t* out_n_aux, int32_t* out_status, float* out_sample, void* stream)
+{
+    IREC_ENSURE_INIT();
+    k_gp_finish<<<std::max(1, std::min((D + 255) / 256, 64)), 256, 0, (cudaStream_t)stream>>>(
+        state, gather_idx, offset, out_indices, out_n_aux, out_status, out_sample);
+    irec_count_launch();
+    return irec_check_launch("k_gp_finish");
+}
+
+int irec_topb_merge(const irec_record_t* records, int n_records, int Bcur, int B, irec_record_t* out_records,
+                    int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (n_records <= 0 || B <= 0 || B > 32) return irec_fail(IREC_E_INVALID, "topb_merge: bad sizes");
+    if (workspace_bytes < (sizeof(float) + sizeof(int32_t)) * (size_t)n_records)
+        return irec_fail(IREC_E_CAPACITY, "topb_merge: workspace too small");
+    float* g_sc = reinterpret_cast<float*>(workspace);
+    int32_t* g_id = reinterpret_cast<int32_t*>(g_sc + n_records);
+    k_topb_merge<<<1, 256, 0, (cudaStream_t)stream>>>(records, nullptr, 1, n_records, nullptr, Bcur, B, out_records, out_count,
+                                                      g_sc, g_id);
+    irec_count_launch();
+    return irec_check_launch("k_topb_merge");
+}
+
+// ---------------- the block-batched entry point ------------------------------------------------
+size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, int B, int max_aux)
+{
+    if (irec_init() != IREC_OK) return 0;
+    const int bmax = pick_bmax(B) > 0 ? pick_bmax(B) : 32;
+    const size_t resident = sizeof(int2) * (size_t)irec_device().sm_count * (size_t)max_aux * bmax + 256;
+    const size_t general = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256 + sizeof(irec_record_t) * 32 + 256 +
+                           irec_beam_step_workspace_bytes((int)max_block_dim, B);
+    (void)nb; (void)S;
+    return std::max(resident, general);
+}
+
+int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                     const int64_t* gather_idx, const int64_t* block_offsets, int nb, int64_t max_block_dim,
+                     float omega, int S, int B, int64_t seed,
+                     int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status,
+                     float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nb <= 0) return IREC_OK;
+    if (S <= 0 || B <= 0 || max_aux <= 0 || max_block_dim <= 0) return irec_fail(IREC_E_INVALID, "beam_encode: bad sizes");
+    if (B > 32) return irec_fail(IREC_E_CAPACITY, "beam_encode: n_beams > 32 is not supported");
+    if ((int64_t)S * B >= (1LL << 31)) return irec_fail(IREC_E_CAPACITY, "beam_encode: S*B must be < 2^31");
+    if (workspace_bytes < irec_beam_encode_workspace_bytes(nb, max_block_dim, S, B, max_aux))
+        return irec_fail(IREC_E_CAPACITY, "beam_encode: workspace too small");
+    if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "beam_encode: kl_per_partition must be > 0");
+
+    const ResidentPlan plan = irec_force_general() ? ResidentPlan{} : plan_resident(nb, (int)max_block_dim, S, B);
+    if (plan.ok) {
+        int* counter = reinterpret_cast<int*>(workspace);
+        if (cudaMemsetAsync(counter, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+        ResidentArgs a;
+        a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
+        a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
+        a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
+        a.out_sample = out_sample; a.T = irec_device().d_T; a.ratio_tab = irec_device().d_ratio;
+        a.ratio_len = irec_device().ratio_len;
+        a.hist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+        a.work_counter = counter; a.DPmax = plan.DPmax; a.NC = plan.NC;
+        launch_resident(plan, a, s);
+        return irec_check_launch("k_beam_encode_resident");
+    }
+
+    // general path: block by block, partition by partition (host needs n_aux: one sync per block)
+    std::vector<int64_t> offs(nb + 1);
+    if (cudaMemcpyAsync(offs.data(), block_offsets, sizeof(int64_t) * (nb + 1), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return irec_fail(IREC_E_CUDA, "beam_encode: reading block offsets failed");
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    void* state = w;
+    const size_t sb = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256;
+    irec_record_t* recs = reinterpret_cast<irec_record_t*>(w + sb);
+    int32_t* rcnt = reinterpret_cast<int32_t*>(recs + 32);
+    void* step_ws = w + sb + sizeof(irec_record_t) * 32 + 256;
+    const size_t step_ws_bytes = irec_beam_step_workspace_bytes((int)max_block_dim, B);
+    for (int blk = 0; blk < nb; ++blk) {
+        const int D = (int)(offs[blk + 1] - offs[blk]);
+        if (D <= 0 || D > max_block_dim) return irec_fail(IREC_E_INVALID, "beam_encode: block size out of range");
+        int rc = irec_beam_state_init(state, t_loc, t_scale, p_loc, p_scale, gather_idx, offs[blk], D, omega, S, B, max_aux, seed, s);
+        if (rc != IREC_OK) return rc;
+        int32_t n_aux = 0, status = 0;
+        rc = irec_beam_state_query(state, &n_aux, &status, nullptr, s);
+        if (rc != IREC_OK) return rc;
+        if (status == IREC_BLK_OK) {
+            for (int t = 0; t < n_aux; ++t) {
+                rc = irec_beam_step_score(state, D, B, t, 0, S, 1, recs, rcnt, step_ws, step_ws_bytes, s);
+                if (rc != IREC_OK) return rc;
+                rc = irec_beam_step_commit(state, D, B, t, recs, rcnt, 1, step_ws, step_ws_bytes, s);
+                if (rc != IREC_OK) return rc;
+            }
+        }
+        rc = irec_beam_state_finish(state, D, gather_idx, offs[blk], out_indices + (size_t)blk * max_aux, out_n_aux + blk,
+                                    out_status + blk, out_sample, s);
+        if (rc != IREC_OK) return rc;
+    }
+    return IREC_OK;
+}
+
+}  // extern "C"

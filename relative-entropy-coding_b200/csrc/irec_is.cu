@@ -1,0 +1,469 @@
+// irec_is.cu -- importance-sampling sampler and the GaussianCoder auxiliary-variable loop (sm_100a).
+//
+// Reference path being replaced: rec/coding/importance_sampling.py:9-103 (alpha = inf branch),
+// rec/coding/samplers.py:61-101 (ImportanceSampler) and rec/coding/coder.py:493-584
+// (GaussianCoder.encode_block / decode_block with the closed-form conditioning of coder.py:141-171).
+//
+// Candidates are the float32 N(0,1) stream of tf.random.normal (Philox4x32-10 + Box-Muller), element
+// j = s*D + d.  Canonical score of sample s:  sum_d (A d + E) d,  d = z - mu',  A = 0.5 (1 - 1/sigma'^2),
+// E = mu'  (= log N(z; mu', sigma') - log N(z; 0, 1) up to a constant), 32-dim chunk sums combined by a
+// pairwise tree -- the same reduction contract as the beam path.
+#include "irec_beam.cuh"
+#include "irec_host.h"
+
+// per-lane chunk sum: 32 dims starting at chunk's first dim; A4/M4 in CI layout (q0 = first quad index)
+__device__ __forceinline__ float is_score_chunk(const float4* __restrict__ A4, const float4* __restrict__ M4, int P, int q0,
+                                                const TfStream& st, uint64_t j_base)
+{
+    float acc = 0.f;
+    const bool aligned = (j_base & 3) == 0;
+#pragma unroll 1
+    for (int iq = 0; iq < 8; ++iq) {
+        float4 z;
+        if (aligned) {
+            z = tf_normal_group(st, (j_base >> 2) + iq);
+        } else {
+            const uint64_t j = j_base + 4 * iq;
+            z.x = tf_normal_elem(st, j); z.y = tf_normal_elem(st, j + 1);
+            z.z = tf_normal_elem(st, j + 2); z.w = tf_normal_elem(st, j + 3);
+        }
+        const float4 A = A4[q0 + iq * P], M = M4[q0 + iq * P];
+        float d, t;
+        d = __fadd_rn(z.x, -M.x); t = __fmaf_rn(A.x, d, M.x); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z.y, -M.y); t = __fmaf_rn(A.y, d, M.y); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z.z, -M.z); t = __fmaf_rn(A.z, d, M.z); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z.w, -M.w); t = __fmaf_rn(A.w, d, M.w); acc = __fmaf_rn(t, d, acc);
+    }
+    return acc;
+}
+
+// canonical score of sample s for the P lanes of its group (all lanes of the warp must call)
+__device__ __forceinline__ float is_score_sample(const float4* A4, const float4* M4, const BeamGeom& g, int lg,
+                                                 const TfStream& st, uint64_t s)
+{
+    if (g.nslots == 1) {
+        float acc = is_score_chunk(A4, M4, g.P, lg, st, s * (uint64_t)g.D + (uint64_t)(32 * lg));
+        for (int stride = 1; stride < g.P; stride <<= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, stride));
+        return acc;
+    }
+    float stack[12];
+    float acc = 0.f;
+    for (int m = 0; m < g.nslots; ++m) {
+        acc = is_score_chunk(A4, M4, 32, m * 256 + lg, st, s * (uint64_t)g.D + (uint64_t)(1024 * m + 32 * lg));
+        for (int stride = 1; stride < 32; stride <<= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, stride));
+        int lvl = 0;
+        while ((m >> lvl) & 1) { acc = __fadd_rn(stack[lvl], acc); ++lvl; }
+        stack[lvl] = acc;
+    }
+    bool have = false;
+    for (int lvl = 0; lvl < 12; ++lvl)
+        if ((g.nslots >> lvl) & 1) { acc = have ? __fadd_rn(stack[lvl], acc) : stack[lvl]; have = true; }
+    return acc;
+}
+
+// standardised target -> canonical coefficients.  mu' = (tl - pl)/ps, sigma' = ts/ps  (importance_sampling.py:41-42)
+__device__ __forceinline__ void is_coeffs(float tl, float ts, float pl, float ps, float& A, float& M)
+{
+    const float mu = __fdiv_rn(__fadd_rn(tl, -pl), ps);
+    const float sg = __fdiv_rn(ts, ps);
+    const double s2 = __dmul_rn((double)sg, (double)sg);
+    A = (float)__dmul_rn(0.5, __dsub_rn(1.0, __ddiv_rn(1.0, s2)));
+    M = mu;
+}
+
+// CTA-wide arg-best of (score desc, s asc); every thread passes its own best; result broadcast
+__device__ __forceinline__ void block_argbest(float& v, int64_t& s, float* s_v, int64_t* s_s)
+{
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, stride);
+        const int64_t os = __shfl_xor_sync(0xffffffffu, s, stride);
+        if (cand_better(ov, os, v, s)) { v = ov; s = os; }
+    }
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_v[warp] = v; s_s[warp] = s; }
+    __syncthreads();
+    v = s_v[0]; s = s_s[0];
+    for (int w = 1; w < nw; ++w)
+        if (cand_better(s_v[w], s_s[w], v, s)) { v = s_v[w]; s = s_s[w]; }
+}
+
+#define IS_NEG_INF __int_as_float(0xff800000)
+#define IS_NO_SAMPLE 0x7fffffffffffffffLL
+
+// ---------------------------------------------------------------------------------------------
+// single partition, grid-wide (ImportanceSampler.coded_sample, samplers.py:74-84)
+// workspace: A[DP], M[DP] (CI layout), per-CTA (score, s) records
+// ---------------------------------------------------------------------------------------------
+__global__ void k_is_params(const float* __restrict__ t_loc, const float* __restrict__ t_scale,
+                            const float* __restrict__ p_loc, const float* __restrict__ p_scale, int D, int P, int DP,
+                            float* A, float* M)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DP; i += gridDim.x * blockDim.x) { A[i] = 0.f; M[i] = 0.f; }
+    // (same thread writes the real entry after the zero fill only if it owns it: use a second pass)
+    __syncthreads();
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+        float a, m;
+        is_coeffs(t_loc[d], t_scale[d], p_loc[d], p_scale[d], a, m);
+        const int ci = ci_index(d, P);
+        A[ci] = a; M[ci] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_is_score_grid(const float* __restrict__ A, const float* __restrict__ M, int D,
+                                                       int64_t S, TfStream st, float* out_v, int64_t* out_s)
+{
+    __shared__ float s_v[8];
+    __shared__ int64_t s_s[8];
+    const BeamGeom g = make_geom(D);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lg = lane & (g.P - 1);
+    const float4* A4 = reinterpret_cast<const float4*>(A);
+    const float4* M4 = reinterpret_cast<const float4*>(M);
+    const int64_t nsg = (S + g.SPW - 1) / g.SPW;
+    float bv = IS_NEG_INF;
+    int64_t bs = IS_NO_SAMPLE;
+    for (int64_t sg = (int64_t)blockIdx.x * nw + warp; sg < nsg; sg += (int64_t)gridDim.x * nw) {
+        const int64_t s = sg * g.SPW + lane / g.P;
+        const bool valid = s < S;
+        float v = is_score_sample(A4, M4, g, lg, st, (uint64_t)(valid ? s : 0));
+        v = (v == v) ? v : IS_NEG_INF;
+        if (valid && cand_better(v, s, bv, bs)) { bv = v; bs = s; }
+    }
+    block_argbest(bv, bs, s_v, s_s);
+    if (threadIdx.x == 0) { out_v[blockIdx.x] = bv; out_s[blockIdx.x] = bs; }
+}
+
+// reduce the per-CTA records, emit index and sample = p_scale * z[idx] + p_loc (importance_sampling.py:74-77)
+__global__ void __launch_bounds__(256) k_is_finish(const float* __restrict__ rec_v, const int64_t* __restrict__ rec_s, int nrec,
+                                                   const float* __restrict__ p_loc, const float* __restrict__ p_scale, int D,
+                                                   TfStream st, int64_t* out_index, float* out_sample)
+{
+    __shared__ float s_v[8];
+    __shared__ int64_t s_s[8];
+    float bv = IS_NEG_INF;
+    int64_t bs = IS_NO_SAMPLE;
+    for (int i = threadIdx.x; i < nrec; i += blockDim.x)
+        if (cand_better(rec_v[i], rec_s[i], bv, bs)) { bv = rec_v[i]; bs = rec_s[i]; }
+    block_argbest(bv, bs, s_v, s_s);
+    if (bs == IS_NO_SAMPLE) bs = 0;
+    if (threadIdx.x == 0) *out_index = bs;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float z = tf_normal_elem(st, (uint64_t)bs * (uint64_t)D + (uint64_t)d);
+        out_sample[d] = __fadd_rn(__fmul_rn(p_scale[d], z), p_loc[d]);
+    }
+}
+
+// decode_gaussian_importance_sample (importance_sampling.py:82-103)
+__global__ void k_is_decode_sample(const float* __restrict__ p_loc, const float* __restrict__ p_scale, int D,
+                                   const int64_t* __restrict__ index, TfStream st, float* out_sample)
+{
+    const int64_t idx = *index;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+        const float z = tf_normal_elem(st, (uint64_t)idx * (uint64_t)D + (uint64_t)d);
+        out_sample[d] = __fadd_rn(__fmul_rn(p_scale[d], z), p_loc[d]);
+    }
+}
+
+__global__ void k_is_normal_stream(TfStream st, int64_t start, int64_t n, float* out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = tf_normal_elem(st, (uint64_t)(start + i));
+}
+
+// ---------------------------------------------------------------------------------------------
+// GaussianCoder.encode_block / decode_block with an ImportanceSampler, one CTA per coder-block
+// (coder.py:493-584).  Running target/coder live in shared memory (plain layout), the per-partition
+// coefficients in CI layout.
+// ---------------------------------------------------------------------------------------------
+#define IS_MAX_D 4096
+struct IsBlockArgs {
+    const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
+    const int64_t* gidx; const int64_t* offs; int nb;
+    float omega; int64_t S; int64_t seed;
+    const TfStream* streams;        // [max_aux] stream of coding seed `seed + k`
+    const int64_t* in_indices;      // decode only
+    const int32_t* in_n_idx;        // decode only
+    int64_t* out_indices; int max_aux; int32_t* out_n_idx; int32_t* out_status; float* out_sample;
+    const float* ratio_tab; int ratio_len;
+    int DPmax;
+};
+
+template <bool ENCODE>
+__global__ void __launch_bounds__(256) k_is_block(const IsBlockArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_kl[IS_MAX_D / 32];
+    __shared__ float s_bv[8];
+    __shared__ int64_t s_bs[8];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int DPm = a.DPmax;
+    float* s_tl = reinterpret_cast<float*>(smem_raw);
+    float* s_ts = s_tl + DPm; float* s_pl = s_ts + DPm; float* s_ps = s_pl + DPm;
+    float* s_A = s_ps + DPm; float* s_M = s_A + DPm; float* s_sv = s_M + DPm; float* s_v = s_sv + DPm;
+
+    for (int blk = blockIdx.x; blk < a.nb; blk += gridDim.x) {
+        __syncthreads();
+        const int64_t off = a.offs[blk];
+        const int D = (int)(a.offs[blk + 1] - off);
+        const BeamGeom g = make_geom(D);
+        const int lg = lane & (g.P - 1);
+        for (int i = tid; i < g.DP; i += nt) { s_A[i] = 0.f; s_M[i] = 0.f; }
+        for (int d = tid; d < D; d += nt) {
+            const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+            s_pl[d] = a.p_loc[gi]; s_ps[d] = a.p_scale[gi];
+            if (ENCODE) { s_tl[d] = a.t_loc[gi]; s_ts[d] = a.t_scale[gi]; }
+        }
+        __syncthreads();
+        int n_idx;
+        if (ENCODE) {
+            // KL and n_aux (coder.py:499-501), canonical float64 chunk/tree sum
+            for (int c = tid; c < g.nch; c += nt) {
+                double acc = 0.0;
+                const int hi = min(D, 32 * c + 32);
+                for (int d = 32 * c; d < hi; ++d) {
+                    const double sp = (double)s_ps[d];
+                    const double dl = __dsub_rn(log((double)s_ts[d]), log(sp));
+                    const double dm = __dsub_rn(__ddiv_rn((double)s_tl[d], sp), __ddiv_rn((double)s_pl[d], sp));
+                    const double k = __dsub_rn(__dadd_rn(__dmul_rn(0.5, __dmul_rn(dm, dm)), __dmul_rn(0.5, expm1(__dmul_rn(2.0, dl)))), dl);
+                    acc = __dadd_rn(acc, k);
+                }
+                s_kl[c] = acc;
+            }
+            {
+                const int Pn = next_pow2_int(g.nch);
+                __syncthreads();
+                for (int stride = 1; stride < Pn; stride <<= 1) {
+                    for (int i = tid * 2 * stride; i + stride < g.nch; i += nt * 2 * stride) s_kl[i] = __dadd_rn(s_kl[i], s_kl[i + stride]);
+                    __syncthreads();
+                }
+            }
+            const float klf = (float)s_kl[0];
+            const float q = __fdiv_rn(klf, a.omega);
+            int n_aux = (!(q == q) || isinf(q)) ? -1 : (int)ceilf(q);
+            int status = IREC_BLK_OK;
+            if (n_aux < 0) status = IREC_BLK_BAD_KL;
+            n_idx = n_aux > 1 ? n_aux : 1;
+            if (status == IREC_BLK_OK && (n_idx > a.max_aux || n_idx > a.ratio_len)) status = IREC_BLK_TOO_LONG;
+            if (tid == 0) { a.out_n_idx[blk] = n_idx; a.out_status[blk] = status; }
+            if (status != IREC_BLK_OK) continue;
+        } else {
+            n_idx = a.in_n_idx[blk];
+            if (n_idx < 1 || n_idx > a.max_aux || n_idx > a.ratio_len) continue;
+        }
+        const int64_t* in_idx = ENCODE ? nullptr : a.in_indices + (size_t)blk * a.max_aux;
+        int64_t* out_idx = ENCODE ? a.out_indices + (size_t)blk * a.max_aux : nullptr;
+
+        // partitions k = 0 .. n_idx-1 ; k < n_idx-1 are auxiliary variables i = n_idx-1-k, the last is final
+        for (int k = 0; k < n_idx; ++k) {
+            const bool final_part = (k == n_idx - 1);
+            const TfStream st = a.streams[k];
+            // --- parameters of this partition's (target, coder) pair ---
+            for (int d = tid; d < D; d += nt) {
+                const float ps = s_ps[d];
+                float sv, v = 0.f;
+                if (!final_part) {
+                    const float cv = __fmul_rn(ps, ps);
+                    v = __fmul_rn(a.ratio_tab[n_idx - 1 - k], cv);
+                    sv = __fsqrt_rn(v);
+                } else {
+                    sv = ps;
+                }
+                s_sv[d] = sv; s_v[d] = v;
+                if (ENCODE) {
+                    float tl_e, ts_e, pl_e;
+                    if (!final_part) {
+                        // get_auxiliary_target (coder.py:147-154), coder loc of the auxiliary coder is 0
+                        const float cv = __fmul_rn(ps, ps), tv = __fmul_rn(s_ts[d], s_ts[d]);
+                        tl_e = __fdiv_rn(__fmul_rn(__fadd_rn(s_tl[d], -s_pl[d]), v), cv);
+                        const float var = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(v, v)), __fmul_rn(cv, cv)),
+                                                    __fdiv_rn(__fmul_rn(v, __fadd_rn(cv, -v)), cv));
+                        ts_e = __fsqrt_rn(var);
+                        pl_e = 0.f;
+                    } else {
+                        tl_e = s_tl[d]; ts_e = s_ts[d]; pl_e = s_pl[d];
+                    }
+                    float A, M;
+                    is_coeffs(tl_e, ts_e, pl_e, sv, A, M);
+                    const int ci = ci_index(d, g.P);
+                    s_A[ci] = A; s_M[ci] = M;
+                }
+            }
+            __syncthreads();
+            // --- choose the index ---
+            int64_t idx;
+            if (ENCODE) {
+                const float4* A4 = reinterpret_cast<const float4*>(s_A);
+                const float4* M4 = reinterpret_cast<const float4*>(s_M);
+                const int64_t nsg = (a.S + g.SPW - 1) / g.SPW;
+                float bv = IS_NEG_INF;
+                int64_t bs = IS_NO_SAMPLE;
+                for (int64_t sg = warp; sg < nsg; sg += nw) {
+                    const int64_t s = sg * g.SPW + lane / g.P;
+                    const bool valid = s < a.S;
+                    float v = is_score_sample(A4, M4, g, lg, st, (uint64_t)(valid ? s : 0));
+                    v = (v == v) ? v : IS_NEG_INF;
+                    if (valid && cand_better(v, s, bv, bs)) { bv = v; bs = s; }
+                }
+                block_argbest(bv, bs, s_bv, s_bs);
+                idx = (bs == IS_NO_SAMPLE) ? 0 : bs;
+                if (tid == 0) out_idx[k] = idx;
+            } else {
+                idx = in_idx[k];
+            }
+            // --- sample of this partition and conditioning (coder.py:157-171, 533-540) ---
+            for (int d = tid; d < D; d += nt) {
+                const float z = tf_normal_elem(st, (uint64_t)idx * (uint64_t)D + (uint64_t)d);
+                if (final_part) {
+                    const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                    a.out_sample[gi] = __fadd_rn(__fmul_rn(s_ps[d], z), s_pl[d]);
+                } else {
+                    const float av = __fadd_rn(__fmul_rn(s_sv[d], z), 0.f);
+                    const float ps = s_ps[d], pl = s_pl[d], v = s_v[d];
+                    const float cv = __fmul_rn(ps, ps);
+                    if (ENCODE) {
+                        const float tl = s_tl[d], ts = s_ts[d];
+                        const float tv = __fmul_rn(ts, ts);
+                        const float cmv = __fadd_rn(cv, -v);
+                        const float num = __fadd_rn(__fmul_rn(__fmul_rn(av, tv), cv),
+                                                    __fmul_rn(__fmul_rn(__fadd_rn(tl, -pl), cmv), cv));
+                        const float den = __fadd_rn(__fmul_rn(tv, v), __fmul_rn(cv, cmv));
+                        s_tl[d] = __fadd_rn(pl, __fdiv_rn(num, den));
+                        const float nvar = __fdiv_rn(__fmul_rn(__fmul_rn(tv, cv), cmv),
+                                                     __fadd_rn(__fmul_rn(v, tv), __fmul_rn(cv, cmv)));
+                        s_ts[d] = __fsqrt_rn(nvar);
+                    }
+                    s_pl[d] = __fadd_rn(pl, av);
+                    s_ps[d] = __fsqrt_rn(__fadd_rn(cv, -v));
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static TfStream is_stream_for_seed(int64_t seed) { return tf_stream_seeded(seed, irec_tf_op_seed(seed)); }
+
+extern "C" {
+
+int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (n <= 0) return IREC_OK;
+    k_is_normal_stream<<<(int)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, (cudaStream_t)stream>>>(is_stream_for_seed(seed), start, n, out);
+    irec_count_launch();
+    return irec_check_launch("k_is_normal_stream");
+}
+
+size_t irec_is_workspace_bytes(int D)
+{
+    if (irec_init() != IREC_OK) return 0;
+    const BeamGeom g = make_geom(D);
+    const int grid_max = irec_device().sm_count * 8;
+    return sizeof(float) * 2 * (size_t)g.DP + (sizeof(float) + sizeof(int64_t)) * (size_t)grid_max + 256;
+}
+
+int irec_is_coded_sample(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                         int D, int64_t S, int64_t seed, int64_t* out_index, float* out_sample,
+                         void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D <= 0 || S <= 0) return irec_fail(IREC_E_INVALID, "is_coded_sample: bad sizes");
+    if (workspace_bytes < irec_is_workspace_bytes(D)) return irec_fail(IREC_E_CAPACITY, "is_coded_sample: workspace too small");
+    const BeamGeom g = make_geom(D);
+    const int grid_max = irec_device().sm_count * 8;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    int64_t* rec_s = reinterpret_cast<int64_t*>(w);
+    float* A = reinterpret_cast<float*>(rec_s + grid_max + 8);
+    float* M = A + g.DP;
+    float* rec_v = M + g.DP;
+    const TfStream st = is_stream_for_seed(seed);
+    k_is_params<<<1, 1024, 0, s>>>(t_loc, t_scale, p_loc, p_scale, D, g.P, g.DP, A, M);
+    irec_count_launch();
+    const int64_t nsg = (S + g.SPW - 1) / g.SPW;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nsg + 7) / 8, grid_max));
+    k_is_score_grid<<<grid, 256, 0, s>>>(A, M, D, S, st, rec_v, rec_s);
+    irec_count_launch();
+    k_is_finish<<<1, 256, 0, s>>>(rec_v, rec_s, grid, p_loc, p_scale, D, st, out_index, out_sample);
+    irec_count_launch();
+    return irec_check_launch("irec_is_coded_sample");
+}
+
+int irec_is_decode_sample(const float* p_loc, const float* p_scale, int D, const int64_t* index, int64_t seed,
+                          float* out_sample, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (D <= 0) return irec_fail(IREC_E_INVALID, "is_decode_sample: bad sizes");
+    k_is_decode_sample<<<std::max(1, std::min((D + 255) / 256, 256)), 256, 0, (cudaStream_t)stream>>>(
+        p_loc, p_scale, D, index, is_stream_for_seed(seed), out_sample);
+    irec_count_launch();
+    return irec_check_launch("k_is_decode_sample");
+}
+
+size_t irec_is_block_workspace_bytes(int max_aux) { return sizeof(TfStream) * (size_t)std::max(max_aux, 1) + 256; }
+
+static int is_block_common(bool encode, IsBlockArgs& a, int64_t max_block_dim, int max_aux, int64_t seed, void* workspace,
+                           size_t workspace_bytes, cudaStream_t s)
+{
+    if (max_block_dim <= 0 || max_block_dim > IS_MAX_D)
+        return irec_fail(IREC_E_CAPACITY, "importance-sampler blocks support at most 4096 dims per block (use block_size)");
+    if (max_aux <= 0) return irec_fail(IREC_E_INVALID, "is block: max_aux must be > 0");
+    if (workspace_bytes < irec_is_block_workspace_bytes(max_aux)) return irec_fail(IREC_E_CAPACITY, "is block: workspace too small");
+    std::vector<TfStream> streams((size_t)max_aux);
+    for (int k = 0; k < max_aux; ++k) streams[k] = is_stream_for_seed(seed + k);
+    if (cudaMemcpyAsync(workspace, streams.data(), sizeof(TfStream) * (size_t)max_aux, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return irec_fail(IREC_E_CUDA, "is block: stream table upload failed");
+    if (cudaStreamSynchronize(s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "is block: sync failed");
+    a.streams = reinterpret_cast<const TfStream*>(workspace);
+    a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
+    const BeamGeom g = make_geom((int)max_block_dim);
+    a.DPmax = g.DP;
+    const size_t smem = sizeof(float) * 8 * (size_t)g.DP;
+    const int grid = std::min(a.nb, irec_device().sm_count * 2);
+    if (encode) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_is_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
+        k_is_block<true><<<grid, 256, smem, s>>>(a);
+    } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_is_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
+        k_is_block<false><<<grid, 256, smem, s>>>(a);
+    }
+    irec_count_launch();
+    return irec_check_launch("k_is_block");
+}
+
+int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                   const int64_t* gather_idx, const int64_t* block_offsets, int nb, int64_t max_block_dim,
+                   float omega, int64_t S, int64_t seed,
+                   int64_t* out_indices, int max_aux, int32_t* out_n_idx, int32_t* out_status,
+                   float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (nb <= 0) return IREC_OK;
+    if (S <= 0 || !(omega > 0.f)) return irec_fail(IREC_E_INVALID, "is_encode: bad arguments");
+    IsBlockArgs a{};
+    a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale; a.gidx = gather_idx; a.offs = block_offsets;
+    a.nb = nb; a.omega = omega; a.S = S; a.seed = seed; a.out_indices = out_indices; a.max_aux = max_aux;
+    a.out_n_idx = out_n_idx; a.out_status = out_status; a.out_sample = out_sample;
+    return is_block_common(true, a, max_block_dim, max_aux, seed, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int irec_is_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
+                   const int64_t* block_offsets, int nb, int64_t max_block_dim, int64_t seed,
+                   const int64_t* indices, int max_aux, const int32_t* n_idx,
+                   float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (nb <= 0) return IREC_OK;
+    IsBlockArgs a{};
+    a.p_loc = p_loc; a.p_scale = p_scale; a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb;
+    a.seed = seed; a.in_indices = indices; a.in_n_idx = n_idx; a.max_aux = max_aux; a.out_sample = out_sample;
+    return is_block_common(false, a, max_block_dim, max_aux, seed, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

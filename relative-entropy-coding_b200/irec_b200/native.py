@@ -1,0 +1,131 @@
+"""ctypes binding of libirec.so (the C ABI declared in include/irec.h).
+
+PyTorch is used only as the owner of device memory and streams: tensors are handed to the library
+as raw device pointers (`tensor.data_ptr()`), together with the current CUDA stream.  There is no
+CPU fallback: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libirec.so")
+
+IREC_OK = 0
+BLK_OK, BLK_BAD_KL, BLK_TOO_LONG = 0, 1, 2
+RECORD_BYTES = 16
+
+
+class NativeError(RuntimeError):
+    """libirec.so is missing / failed; never silently replaced by a CPU path."""
+
+
+_lib = None
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+_SIGNATURES = {
+    "irec_version": (C.c_int, []),
+    "irec_last_error_string": (C.c_char_p, []),
+    "irec_init": (C.c_int, []),
+    "irec_get_ndtri_table": (C.c_int, [_vp]),
+    "irec_aux_ratio": (C.c_float, [_i32]),
+    "irec_tf_op_seed": (C.c_int64, [_i64]),
+    "irec_split_permutation": (C.c_int, [_i64, _i64, _vp]),
+    "irec_beam_uniform_int": (C.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "irec_is_normal_stream": (C.c_int, [_i64, _i64, _i64, _vp, _vp]),
+    "irec_kl_naux": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp]),
+    "irec_beam_encode_workspace_bytes": (C.c_size_t, [_i32, _i64, _i32, _i32, _i32]),
+    "irec_beam_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i32, _i32, _i64,
+                                   _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "irec_beam_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "irec_beam_state_bytes": (C.c_size_t, [_i32, _i32, _i32]),
+    "irec_beam_state_init": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i64, _vp]),
+    "irec_beam_state_query": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "irec_beam_step_workspace_bytes": (C.c_size_t, [_i32, _i32]),
+    "irec_beam_step_score": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "irec_beam_step_commit": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "irec_beam_state_finish": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "irec_topb_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "irec_is_workspace_bytes": (C.c_size_t, [_i32]),
+    "irec_is_coded_sample": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "irec_is_decode_sample": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "irec_is_block_workspace_bytes": (C.c_size_t, [_i32]),
+    "irec_is_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i64, _i64,
+                                 _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "irec_is_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "irec_launch_count": (C.c_int64, []),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+def load_library():
+    """dlopen libirec.so and declare every prototype (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def lib():
+    l = load_library()
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device: the iREC coders run on B200 (sm_100a) only; there is no CPU fallback")
+    return l
+
+
+def check(rc, what=""):
+    if rc != IREC_OK:
+        msg = load_library().irec_last_error_string().decode(errors="replace")
+        raise NativeError(f"{what or 'libirec'} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """raw device pointer of a CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise NativeError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(load_library().irec_launch_count())
+
+
+def tf_op_seed(seed):
+    return int(load_library().irec_tf_op_seed(int(seed)))
+
+
+def aux_ratio(i):
+    return float(load_library().irec_aux_ratio(int(i)))
+
+
+def split_permutation(n, seed):
+    """Coder.split permutation (rec/coding/coder.py:60-67) as a CPU int64 tensor (host C++ in libirec.so)."""
+    out = torch.empty(int(n), dtype=torch.int64)
+    check(load_library().irec_split_permutation(int(n), int(seed), C.c_void_p(out.data_ptr())), "irec_split_permutation")
+    return out
+
+
+def ndtri_table():
+    out = torch.empty(10007, dtype=torch.float32)
+    check(lib().irec_get_ndtri_table(C.c_void_p(out.data_ptr())), "irec_get_ndtri_table")
+    return out

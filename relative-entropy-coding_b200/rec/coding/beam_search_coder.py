@@ -1,0 +1,108 @@
+"""rec.coding.beam_search_coder -- BeamSearchCoder with the reference's interface
+(reference: rec/coding/beam_search_coder.py:13-151) on the sm_100a kernels of libirec.so.
+
+Per coder-block the whole loop of the reference's `encode_block` (schedule, shared-seed candidate
+generation, hash mixing, quantile, log-weights, top-B, beam update; reference :53-122) runs inside
+one persistent CTA; `encode()` launches all blocks of a tensor at once.
+"""
+import numpy as np
+import torch
+
+from irec_b200 import engine as E
+from rec.coding.coder import GaussianCoder, _dist_tensors
+from rec.coding.utils import CodingError
+
+
+class BeamSearchCoder(GaussianCoder):
+
+    def __init__(self, kl_per_partition, n_beams, extra_samples=1., extrapolate_auxiliary_ratios=True,
+                 name="gaussian_encoder", **kwargs):
+        super().__init__(name=name, kl_per_partition=kl_per_partition, sampler=None,
+                         extrapolate_auxiliary_ratios=extrapolate_auxiliary_ratios, **kwargs)
+        self.n_beams = int(n_beams)
+        self.n_samples = int(np.exp(kl_per_partition * extra_samples))       # reference :29 (Omega in nats, truncation)
+        self.big_prime = 10007
+        if self.n_beams < 1 or self.n_samples < 1:
+            raise CodingError("n_beams and the number of samples per partition must be at least 1")
+
+    def _uses_kernels(self):
+        return True
+
+    # reference :33-35 (kept for API parity; the kernels keep the running sums incrementally)
+    def simple_hash(self, matrix):
+        m = torch.as_tensor(matrix, dtype=torch.int32)
+        w = torch.arange(69, 69 + m.shape[1], dtype=torch.int32)
+        return torch.remainder((m * w).sum(dim=1, dtype=torch.int32), self.big_prime - 1) + 1
+
+    def _encode_flat(self, tl, ts, pl, ps, gather, offsets, nb, max_dim, seed):
+        res = E.beam_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition, self.n_samples,
+                                   self.n_beams, seed)
+        return res.indices, res.sample
+
+    def _decode_flat(self, pl, ps, gather, offsets, nb, max_dim, seed, indices):
+        return E.beam_decode_blocks(pl, ps, gather, offsets, nb, self.n_samples, seed, indices)
+
+    def encode_block(self, target_dist, coding_dist, seed, update_sampler=False, numpy=True):
+        if target_dist.loc.shape[0] != 1:
+            raise CodingError("For encoding, batch size must be 1.")
+        self._check_ratios()
+        tl, ts = _dist_tensors(target_dist)
+        pl, ps = _dist_tensors(coding_dist)
+        shape = tl.shape
+        offsets, nb, max_dim = E.make_block_offsets(tl.numel(), None, tl.device)
+        indices, sample = self._encode_flat(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), None,
+                                            offsets, nb, max_dim, seed)
+        return indices[0], sample.reshape(shape)
+
+    def decode_block(self, coding_dist, indices, seed):
+        self._check_ratios()
+        pl, ps = _dist_tensors(coding_dist)
+        shape = pl.shape
+        offsets, nb, max_dim = E.make_block_offsets(pl.numel(), None, pl.device)
+        indices.reverse()                  # reference :127 reverses the caller's list in place
+        sample = self._decode_flat(pl.reshape(-1), ps.reshape(-1), None, offsets, nb, max_dim, seed, [indices[::-1]])
+        return sample.reshape(shape)
+
+    def get_codelength(self, indicies):
+        return len(indicies) * np.log(self.n_samples)               # reference :150-151
+
+    # -- extension: a batch of independent tensors (e.g. images) in one launch ----------------------
+    def encode_batch(self, target_dist, coding_dist, seed):
+        """Codes every row of a [N, ...] batch independently with the same coding seed -- what looping the
+        reference's `encode` over N single-image batches computes.  Returns (indices[N][n_blocks][n_aux], sample)."""
+        self._check_ratios()
+        tl, ts = _dist_tensors(target_dist)
+        pl, ps = _dist_tensors(coding_dist)
+        shape = tl.shape
+        n_items = shape[0]
+        n = tl[0].numel()
+        gather = None
+        if self.block_size is not None:
+            perm = self._permutation(n, seed, tl.device)
+            gather = (perm[None, :] + torch.arange(n_items, device=tl.device)[:, None] * n).reshape(-1).contiguous()
+        offsets, nb, max_dim = E.make_block_offsets(n, self.block_size, tl.device, n_items=n_items)
+        indices, sample = self._encode_flat(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), gather,
+                                            offsets, nb, max_dim, seed)
+        per = nb // n_items
+        if self.block_size is None:
+            nested = [indices[i] for i in range(n_items)]
+        else:
+            nested = [indices[i * per:(i + 1) * per] for i in range(n_items)]
+        return nested, sample.reshape(shape)
+
+    def decode_batch(self, coding_dist, indices, seed):
+        self._check_ratios()
+        pl, ps = _dist_tensors(coding_dist)
+        shape = pl.shape
+        n_items = shape[0]
+        n = pl[0].numel()
+        gather = None
+        if self.block_size is not None:
+            perm = self._permutation(n, seed, pl.device)
+            gather = (perm[None, :] + torch.arange(n_items, device=pl.device)[:, None] * n).reshape(-1).contiguous()
+            flat_idx = [blk for item in indices for blk in item]
+        else:
+            flat_idx = list(indices)
+        offsets, nb, max_dim = E.make_block_offsets(n, self.block_size, pl.device, n_items=n_items)
+        sample = self._decode_flat(pl.reshape(-1), ps.reshape(-1), gather, offsets, nb, max_dim, seed, flat_idx)
+        return sample.reshape(shape)

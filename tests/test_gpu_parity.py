@@ -1,0 +1,317 @@
+"""GPU parity tests (run on a B200 with -m gpu): every CUDA path, through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bar: bit-exact indices, bit-exact samples, bit-exact decode."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda(built):
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    from irec_b200 import native
+    native.lib()
+    return torch.device("cuda:0")
+
+
+def bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def to_dev(arrs, dev):
+    import torch
+    return [torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous() for a in arrs]
+
+
+# ------------------------------------------------------------------------------------------ tables / streams
+def test_ndtri_table_bit_exact(cuda):
+    from irec_b200 import native
+    T = native.ndtri_table().numpy()
+    assert np.array_equal(bits(T[1:]), bits(O.ndtri_table()[1:]))
+
+
+@pytest.mark.parametrize("q,start,n", [(42, 0, 4096), (43, 5, 1001), (69420, 123457, 3000), (0, 0, 64),
+                                        (2 ** 31 - 1, 0, 64), (2 ** 33 + 7, 3, 64)])
+def test_uniform_int_stream(cuda, q, start, n):
+    from irec_b200 import engine
+    r = engine.beam_uniform_int(q, start, n).cpu().numpy()
+    assert np.array_equal(r, O.beam_uniform_int(q, start, n))
+
+
+@pytest.mark.parametrize("seed,start,n", [(42, 0, 8192), (69420, 7, 1001), (0, 0, 256)])
+def test_normal_stream(cuda, seed, start, n):
+    from irec_b200 import engine
+    z = engine.is_normal_stream(seed, start, n).cpu().numpy()
+    assert np.array_equal(bits(z), bits(O.is_normal_stream(seed, start, n)))
+
+
+def test_kl_naux(cuda):
+    import torch
+    from irec_b200 import engine
+    tl, ts, pl, ps = synth.c2(8192, data_seed=3)
+    d = to_dev((tl, ts, pl, ps), cuda)
+    offs, nb, _ = engine.make_block_offsets(8192, 1000, cuda)
+    kl, na = engine.kl_naux(*d, None, offs, nb, 3.0)
+    kl, na = kl.cpu().numpy(), na.cpu().numpy()
+    for b in range(nb):
+        lo, hi = 1000 * b, min(8192, 1000 * b + 1000)
+        ok = O.kl(tl[lo:hi], ts[lo:hi], pl[lo:hi], ps[lo:hi])
+        assert bits(kl[b]) == bits(np.float32(ok))
+        assert na[b] == O.n_aux(ok, 3.0)
+
+
+# ------------------------------------------------------------------------------------------ beam coder
+BEAM_CASES = [
+    # recipe, D, data_seed, omega, extra, B, seed
+    ("c1", 64, 0, 3.0, 1.2, 1, 42),          # BASELINE config 1
+    ("c1", 64, 0, 3.0, 1.2, 20, 42),
+    ("c1", 64, 1, 3.0, 1.0, 10, 69420),
+    ("c2", 1000, 1, 3.0, 1.2, 20, 42),       # one C2 coder-block
+    ("c2", 192, 2, 3.0, 1.2, 20, 42),        # last C2 block
+    ("c3", 1000, 4, 3.0, 1.0, 10, 7),        # one C3 coder-block
+    ("c3", 288, 3, 3.0, 1.0, 10, 7),
+    ("c3", 56, 5, 3.0, 1.0, 10, 7),
+    ("c2", 37, 6, 3.0, 1.2, 5, 1),           # D not a multiple of 4: unaligned Philox quads
+    ("c2", 1, 7, 1.0, 1.0, 3, 1),
+    ("c2", 1023, 8, 4.0, 1.0, 2, 11),
+    ("c2", 257, 9, 2.0, 1.0, 32, 5),         # S=7 < B: the beam count grows 1 -> 7 -> 32
+    ("c2", 100, 10, 5.0, 1.3, 16, 2 ** 31 + 5),
+]
+
+
+def run_beam_case(cuda, recipe, D, data_seed, omega, extra, B, seed):
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    tl, ts, pl, ps = getattr(synth, recipe)(D, data_seed=data_seed)
+    coder = BeamSearchCoder(kl_per_partition=omega, n_beams=B, extra_samples=extra)
+    ref = O.beam_encode_block(tl, ts, pl, ps, omega, coder.n_samples, B, seed)
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    indices, sample = coder.encode(t, p, seed=seed)
+    assert list(indices) == ref["indices"].tolist()
+    assert np.array_equal(bits(sample.cpu().numpy().reshape(-1)), bits(ref["sample"]))
+    assert coder.get_codelength(indices) == len(ref["indices"]) * np.log(coder.n_samples)
+    keep = list(indices)
+    dec = coder.decode(p, indices, seed=seed)
+    assert indices == keep[::-1], "decode_block reverses the caller's list in place (reference :127)"
+    assert torch.equal(dec, sample)
+    odec = O.beam_decode_block(pl, ps, coder.n_samples, seed, ref["indices"])
+    assert np.array_equal(bits(dec.cpu().numpy().reshape(-1)), bits(odec))
+
+
+@pytest.mark.parametrize("case", BEAM_CASES, ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES])
+def test_beam_resident_vs_oracle(cuda, case):
+    os.environ.pop("IREC_FORCE_GENERAL", None)
+    run_beam_case(cuda, *case)
+
+
+@pytest.mark.parametrize("case", BEAM_CASES[:9], ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES[:9]])
+def test_beam_general_path_vs_oracle(cuda, case):
+    os.environ["IREC_FORCE_GENERAL"] = "1"
+    try:
+        run_beam_case(cuda, *case)
+    finally:
+        os.environ.pop("IREC_FORCE_GENERAL", None)
+
+
+def test_beam_large_dim_general_path(cuda):
+    """D > 1024 (no block_size): multi-slot reduction tree"""
+    run_beam_case(cuda, "c2", 2500, 12, 6.0, 1.0, 4, 3)
+
+
+def test_reference_unit_test_case(cuda):
+    """rec/coding/tests/test_coder.py:12-21"""
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    encoder = BeamSearchCoder(kl_per_partition=6., n_beams=10, extra_samples=1.)
+    t = Normal(torch.tensor([[5.1]]), torch.tensor([[0.001]]), device=cuda)
+    p = Normal(torch.tensor([[0.]]), torch.tensor([[1.]]), device=cuda)
+    indices, sample = encoder.encode(t, p, seed=69420, update_sampler=False)
+    ref = O.beam_encode_block([5.1], [0.001], [0.], [1.], 6., 403, 10, 69420)
+    assert list(indices) == ref["indices"].tolist()
+    reconstructed = encoder.decode(p, indices, seed=69420)
+    assert torch.equal(sample, reconstructed)
+    assert abs(float(sample) - 5.1) < 0.01
+
+
+def test_beam_block_size_split(cuda):
+    """whole-tensor encode with block_size: Coder.split permutation + all blocks in one launch (C2 level shape)"""
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    n, bs, seed = 8192, 1000, 42
+    tl, ts, pl, ps = synth.c2(n, data_seed=21)
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=bs)
+    shape = (1, 16, 16, 32)
+    t = Normal(tl.reshape(shape), ts.reshape(shape), device=cuda)
+    p = Normal(pl.reshape(shape), ps.reshape(shape), device=cuda)
+    indices, sample = coder.encode(t, p, seed=seed)
+    assert sample.shape == shape and len(indices) == 9
+    perm = O.shuffle_perm(n, seed)
+    out = np.zeros(n, np.float32)
+    for b in range(9):
+        sel = perm[b * bs:min(n, (b + 1) * bs)]
+        ref = O.beam_encode_block(tl[sel], ts[sel], pl[sel], ps[sel], 3., 36, 20, seed)
+        assert indices[b] == ref["indices"].tolist(), b
+        out[sel] = ref["sample"]
+    assert np.array_equal(bits(sample.cpu().numpy().reshape(-1)), bits(out))
+    dec = coder.decode(p, [list(i) for i in indices], seed=seed)
+    assert torch.equal(dec, sample)
+    # split / merge are inverse of each other and follow the same permutation
+    blocks = coder.split(t.loc, seed=seed)[0]
+    assert np.array_equal(blocks[3].cpu().numpy(), tl[perm[3000:4000]])
+    merged, = coder.merge(blocks, shape=shape, seed=seed)
+    assert torch.equal(merged, t.loc)
+
+
+def test_beam_batch_matches_single(cuda):
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    n, N_img = 2048, 5
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=1000)
+    arrs = [synth.c2(n, data_seed=100 + i) for i in range(N_img)]
+    stack = [np.stack([a[k] for a in arrs]) for k in range(4)]
+    t = Normal(stack[0], stack[1], device=cuda)
+    p = Normal(stack[2], stack[3], device=cuda)
+    idx_b, samp_b = coder.encode_batch(t, p, seed=42)
+    for i in range(N_img):
+        ti = Normal(stack[0][i:i + 1], stack[1][i:i + 1], device=cuda)
+        pi = Normal(stack[2][i:i + 1], stack[3][i:i + 1], device=cuda)
+        idx, samp = coder.encode(ti, pi, seed=42)
+        assert idx == idx_b[i]
+        assert torch.equal(samp[0], samp_b[i])
+    dec = coder.decode_batch(p, idx_b, seed=42)
+    assert torch.equal(dec, samp_b)
+
+
+def test_sharded_block_single_rank(cuda):
+    """candidate-range sharded state machine (world size 1) == oracle"""
+    from irec_b200 import engine
+    mu, sig, pl, ps = synth.c1(64, data_seed=0)
+    d = to_dev((mu, sig, pl, ps), cuda)
+    S = 2000
+    blk = engine.ShardedBeamBlock(64, S, 10, np.log(S) / 1.2, max_aux=64, device=cuda)
+    idx, sample = blk.encode(*d, seed=42)
+    ref = O.beam_encode_block(mu, sig, pl, ps, np.float32(np.log(S) / 1.2), S, 10, 42)
+    assert idx == ref["indices"].tolist()
+    assert np.array_equal(bits(sample.cpu().numpy()), bits(ref["sample"]))
+
+
+def test_errors(cuda):
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    from rec.coding.utils import CodingError
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=4)
+    same = Normal(np.zeros((1, 8)), np.ones((1, 8)), device=cuda)
+    with pytest.raises(CodingError):
+        coder.encode(same, same, seed=1)                 # KL = 0: the reference crashes, we raise CodingError
+    two = Normal(np.zeros((2, 8)), np.ones((2, 8)), device=cuda)
+    with pytest.raises(CodingError):
+        coder.encode(two, two, seed=1)                   # batch size must be 1
+    with pytest.raises(CodingError):
+        BeamSearchCoder(3., 4, block_size=4).split(same.loc, Normal(np.zeros((1, 9)), np.ones((1, 9))).loc)
+    with pytest.raises(CodingError):
+        coder.merge([same.loc.reshape(-1)], shape=None)
+
+
+# ------------------------------------------------------------------------------------------ importance sampler
+@pytest.mark.parametrize("D,coding_bits,seed", [(64, 3 / np.log(2), 42), (1, 8.0, 7), (1000, 5.0, 3), (37, 6.0, 9)])
+def test_is_coded_sample(cuda, D, coding_bits, seed):
+    import torch
+    from irec_b200 import Normal
+    from rec.coding.samplers import ImportanceSampler
+    tl, ts, pl, ps = synth.c2(D, data_seed=D)
+    s = ImportanceSampler(coding_bits=coding_bits)
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    index, sample = s.coded_sample(t, p, seed)
+    oi, osamp = O.is_coded_sample(tl, ts, pl, ps, s.n_samples, seed)
+    assert int(index) == oi
+    assert np.array_equal(bits(sample.cpu().numpy().reshape(-1)), bits(osamp))
+    dec = s.decode_sample(p, index, seed)
+    assert torch.equal(dec, sample)
+
+
+@pytest.mark.parametrize("recipe,D,omega,seed", [("c1", 64, 3.0, 42), ("c2", 1000, 3.0, 5), ("c2", 37, 2.0, 1),
+                                                 ("c2", 2000, 3.0, 8)])
+def test_gaussian_coder_importance(cuda, recipe, D, omega, seed):
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+    tl, ts, pl, ps = getattr(synth, recipe)(D, data_seed=D + 1)
+    s = ImportanceSampler(coding_bits=omega / np.log(2), alpha=np.inf)
+    coder = GaussianCoder(kl_per_partition=omega, sampler=s)
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    indices, sample = coder.encode(t, p, seed=seed)
+    ref = O.is_encode_block(tl, ts, pl, ps, omega, s.n_samples, seed)
+    assert [int(i) for i in indices] == ref["indices"].tolist()
+    assert np.array_equal(bits(sample.cpu().numpy().reshape(-1)), bits(ref["sample"]))
+    dec = coder.decode(p, list(indices), seed=seed)
+    assert torch.equal(dec, sample)
+    assert np.array_equal(bits(dec.cpu().numpy().reshape(-1)), bits(O.is_decode_block(pl, ps, seed, ref["indices"])))
+    assert abs(coder.get_codelength(indices) - len(indices) * omega) < 1e-4
+
+
+def test_gaussian_coder_importance_block_size(cuda):
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+    n, bs, seed = 2500, 1000, 42
+    tl, ts, pl, ps = synth.c2(n, data_seed=33)
+    s = ImportanceSampler(coding_bits=3. / np.log(2))
+    coder = GaussianCoder(kl_per_partition=3., sampler=s, block_size=bs)
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    indices, sample = coder.encode(t, p, seed=seed)
+    perm = O.shuffle_perm(n, seed)
+    out = np.zeros(n, np.float32)
+    for b in range(3):
+        sel = perm[b * bs:min(n, (b + 1) * bs)]
+        ref = O.is_encode_block(tl[sel], ts[sel], pl[sel], ps[sel], 3., s.n_samples, seed)
+        assert [int(i) for i in indices[b]] == ref["indices"].tolist()
+        out[sel] = ref["sample"]
+    assert np.array_equal(bits(sample.cpu().numpy().reshape(-1)), bits(out))
+    dec = coder.decode(p, [list(i) for i in indices], seed=seed)
+    assert torch.equal(dec, sample)
+
+
+def test_generic_sampler_plugin_loop(cuda):
+    """GaussianCoder with a user-defined Sampler plug-in goes through the reference's Python loop and still
+    round-trips (here: a thin subclass that defeats the fused-kernel detection)."""
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+
+    class MySampler(ImportanceSampler):
+        pass
+
+    class Wrapper(MySampler):
+        @property
+        def alpha(self):
+            return float("inf")
+
+        @alpha.setter
+        def alpha(self, v):
+            pass
+
+    mu, sig, pl, ps = synth.c1(64, data_seed=2)
+    coder = GaussianCoder(kl_per_partition=3., sampler=Wrapper(coding_bits=3. / np.log(2)))
+    coder._uses_kernels = lambda: False
+    t = Normal(mu[None, :], sig[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    indices, sample = coder.encode(t, p, seed=42)
+    dec = coder.decode(p, list(indices), seed=42)
+    assert torch.allclose(dec, sample, atol=1e-5)
