@@ -169,7 +169,14 @@ struct ResidentArgs {
 };
 
 template <int BMAX>
-constexpr int resident_max_threads() { return BMAX <= 20 ? 640 : 512; }
+constexpr int resident_max_threads()
+{
+#ifdef IREC_RES_THREADS
+    return IREC_RES_THREADS;
+#else
+    return BMAX <= 10 ? 640 : (BMAX <= 20 ? 576 : 512);
+#endif
+}
 
 template <int BMAX>
 __global__ void __launch_bounds__(resident_max_threads<BMAX>(), 1) k_beam_encode_resident(const ResidentArgs a)
@@ -262,24 +269,25 @@ __global__ void __launch_bounds__(resident_max_threads<BMAX>(), 1) k_beam_encode
             const TfStream st = tf_stream_seeded(a.seed + t, a.seed + t);
             const int32_t* hs = s_hsum + 32 * hb;
             if (Bcur == 1) {
-                uint32_t h[1] = { (uint32_t)hash_from_sum(hs[0]) };
+                BeamHash h[1];
+                h[0].h = (uint32_t)hash_from_sum(hs[0]); h[0].h4 = 4u * h[0].h;
                 float acc[1];
                 for (int sg = warp; sg < nsg; sg += nwarps) {
                     const int s = sg * g.SPW + lane / g.P;
-                    score_sample<1, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, 1, acc);
+                    score_sample<1, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, acc);
                     if (lg == 0 && s < a.S) s_scores[s] = (acc[0] == acc[0]) ? acc[0] : __int_as_float(0xff800000);
                 }
             } else {
-                uint32_t h[BMAX];
+                BeamHash h[BMAX];
 #pragma unroll
-                for (int b = 0; b < BMAX; ++b) h[b] = (uint32_t)hash_from_sum(hs[b]);
+                for (int b = 0; b < BMAX; ++b) {
+                    h[b].h = b < Bcur ? (uint32_t)hash_from_sum(hs[b]) : 0u;
+                    h[b].h4 = 4u * h[b].h;
+                }
                 float acc[BMAX];
                 for (int sg = warp; sg < nsg; sg += nwarps) {
                     const int s = sg * g.SPW + lane / g.P;
-                    if (Bcur == BMAX)
-                        score_sample<BMAX, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, Bcur, acc);
-                    else
-                        score_sample<BMAX, false, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, Bcur, acc);
+                    score_sample<BMAX, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, (uint64_t)min(s, a.S - 1), h, acc);
                     if (lg == 0 && s < a.S) {
 #pragma unroll
                         for (int b = 0; b < BMAX; ++b)
@@ -510,9 +518,12 @@ __global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
     const TfStream st = tf_stream_seeded(hdr->seed + a.t, hdr->seed + a.t);
     const int lg = lane & (g.P - 1);
 
-    uint32_t h[BMAX];
+    BeamHash h[BMAX];
 #pragma unroll
-    for (int b = 0; b < BMAX; ++b) h[b] = (uint32_t)hash_from_sum(b < Bcur ? hs[b] : 0);
+    for (int b = 0; b < BMAX; ++b) {
+        h[b].h = b < Bcur ? (uint32_t)hash_from_sum(hs[b]) : 0u;
+        h[b].h4 = 4u * h[b].h;
+    }
 
     // contiguous range of sample groups per CTA
     const int64_t nsg = (a.s_end - a.s_begin + g.SPW - 1) / g.SPW;
@@ -527,11 +538,9 @@ __global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
         const uint64_t s_eff = (uint64_t)(valid ? s : a.s_begin);
         float acc[BMAX];
         if (g.nslots > 1)
-            score_sample<BMAX, false, true>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
-        else if (Bcur == BMAX)
-            score_sample<BMAX, true, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
+            score_sample<BMAX, true>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, acc);
         else
-            score_sample<BMAX, false, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, Bcur, acc);
+            score_sample<BMAX, false>(s_T, sa4, A4, E4, M4, beams4, g, lg, st, s_eff, h, acc);
         const float tau = *s_tau;
         if (valid && lg == 0) {
 #pragma unroll

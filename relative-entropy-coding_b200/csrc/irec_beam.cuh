@@ -47,42 +47,79 @@ __host__ __device__ __forceinline__ BeamGeom make_geom(int D)
 
 // ---------------------------------------------------------------------------------------------
 // score_chunk: accumulate the canonical chunk sums of candidate sample `s` (stream element base
-// j_base = s*D + first dim of the chunk) against beams b < Bcur.
+// j_base = s*D + first dim of the chunk) against ALL BMAX beam slots (slots >= Bcur carry hq = 0 and
+// are ignored by the caller; there is no branch in the loop).
 //   per dim:  k = (r*h_b) mod 10007; z = T[k]*sa; x = beam_b + z; d = x - m;
 //             acc_b = fma(fma(A, d, E), d, acc_b)
+// Exact modular product in three IMADs: with r' = floor(r * 2^32 / P) (once per element) the quotient
+// q = umulhi(h, r') equals floor(r*h/P) exactly (P prime, so r*h/P is never within 2^-18 of an
+// integer), hence 4k = r*(4h) - q*(4P) is the byte offset into the table.
 // q0 = float4 index of the chunk's first quad inside the CI arrays (slot*8*P + l).
 // ---------------------------------------------------------------------------------------------
-template <int BMAX, bool FULL>
+struct BeamHash {
+    uint32_t h4;   // 4 * h_b  (0 for unused slots)
+    uint32_t h;    // h_b
+};
+
+__device__ __forceinline__ uint32_t shoup_rprime(uint32_t r)
+{
+    return (uint32_t)(((uint64_t)r << 32) / IREC_PRIME);
+}
+
+__device__ __forceinline__ float table_at(const float* __restrict__ T, uint32_t r, uint32_t rp, const BeamHash& bh)
+{
+    const uint32_t q = __umulhi(bh.h, rp);
+    const uint32_t k4 = r * bh.h4 - q * (4u * IREC_PRIME);
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(T) + k4);
+}
+
+template <int BMAX>
+struct BeamGroup {   // beams are processed in groups of G so that G*4 independent chains are in flight
+    static constexpr int G = (BMAX <= 5) ? BMAX : ((BMAX % 5 == 0) ? 5 : 4);
+};
+
+template <int BMAX>
 __device__ __forceinline__ void score_chunk(const float* __restrict__ T,
                                             const float4* __restrict__ sa4, const float4* __restrict__ A4,
                                             const float4* __restrict__ E4, const float4* __restrict__ M4,
                                             const float4* __restrict__ beams4, int beam_stride4, int P, int q0,
-                                            const TfStream& st, uint64_t j_base, const uint32_t (&h)[BMAX],
-                                            int Bcur, float (&acc)[BMAX])
+                                            const TfStream& st, uint64_t j_base, const BeamHash (&h)[BMAX],
+                                            float (&acc)[BMAX])
 {
+    constexpr int G = BeamGroup<BMAX>::G;
     const bool aligned = (j_base & 3) == 0;
 #pragma unroll 1
     for (int iq = 0; iq < 8; ++iq) {
         const uint4 u = aligned ? tf_stream_group(st, (j_base >> 2) + iq) : tf_stream_quad_at(st, j_base + 4 * iq);
         const uint32_t r0 = beam_r_from_u32(u.x), r1 = beam_r_from_u32(u.y);
         const uint32_t r2 = beam_r_from_u32(u.z), r3 = beam_r_from_u32(u.w);
+        const uint32_t p0 = shoup_rprime(r0), p1 = shoup_rprime(r1), p2 = shoup_rprime(r2), p3 = shoup_rprime(r3);
         const int qi = q0 + iq * P;
         const float4 sa = sa4[qi], A = A4[qi], E = E4[qi], M = M4[qi];
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) {
-            if (FULL || b < Bcur) {
-                float4 bm = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (beams4) bm = beams4[b * beam_stride4 + qi];
-                const uint32_t hb = h[b];
-                float x, d, t;
-                x = __fadd_rn(bm.x, __fmul_rn(T[beam_mix(r0, hb)], sa.x));
-                d = __fadd_rn(x, -M.x); t = __fmaf_rn(A.x, d, E.x); acc[b] = __fmaf_rn(t, d, acc[b]);
-                x = __fadd_rn(bm.y, __fmul_rn(T[beam_mix(r1, hb)], sa.y));
-                d = __fadd_rn(x, -M.y); t = __fmaf_rn(A.y, d, E.y); acc[b] = __fmaf_rn(t, d, acc[b]);
-                x = __fadd_rn(bm.z, __fmul_rn(T[beam_mix(r2, hb)], sa.z));
-                d = __fadd_rn(x, -M.z); t = __fmaf_rn(A.z, d, E.z); acc[b] = __fmaf_rn(t, d, acc[b]);
-                x = __fadd_rn(bm.w, __fmul_rn(T[beam_mix(r3, hb)], sa.w));
-                d = __fadd_rn(x, -M.w); t = __fmaf_rn(A.w, d, E.w); acc[b] = __fmaf_rn(t, d, acc[b]);
+        for (int b0 = 0; b0 < BMAX; b0 += G) {
+            float tv[G][4];
+            float4 bm[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                tv[g][0] = table_at(T, r0, p0, h[b0 + g]);
+                tv[g][1] = table_at(T, r1, p1, h[b0 + g]);
+                tv[g][2] = table_at(T, r2, p2, h[b0 + g]);
+                tv[g][3] = table_at(T, r3, p3, h[b0 + g]);
+                bm[g] = beams4[(b0 + g) * beam_stride4 + qi];
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float x, d, t, a = acc[b0 + g];
+                x = __fadd_rn(bm[g].x, __fmul_rn(tv[g][0], sa.x));
+                d = __fadd_rn(x, -M.x); t = __fmaf_rn(A.x, d, E.x); a = __fmaf_rn(t, d, a);
+                x = __fadd_rn(bm[g].y, __fmul_rn(tv[g][1], sa.y));
+                d = __fadd_rn(x, -M.y); t = __fmaf_rn(A.y, d, E.y); a = __fmaf_rn(t, d, a);
+                x = __fadd_rn(bm[g].z, __fmul_rn(tv[g][2], sa.z));
+                d = __fadd_rn(x, -M.z); t = __fmaf_rn(A.z, d, E.z); a = __fmaf_rn(t, d, a);
+                x = __fadd_rn(bm[g].w, __fmul_rn(tv[g][3], sa.w));
+                d = __fadd_rn(x, -M.w); t = __fmaf_rn(A.w, d, E.w); a = __fmaf_rn(t, d, a);
+                acc[b0 + g] = a;
             }
         }
     }
@@ -90,40 +127,39 @@ __device__ __forceinline__ void score_chunk(const float* __restrict__ T,
 
 // canonical pairwise tree over the P chunk sums held by the P lanes of a sample group
 // (xor butterfly: stride 1, 2, 4, ...; a + b == b + a bitwise, so every lane ends with the total)
-template <int BMAX, bool FULL>
-__device__ __forceinline__ void group_tree_sum(float (&acc)[BMAX], int P, int Bcur)
+template <int BMAX>
+__device__ __forceinline__ void group_tree_sum(float (&acc)[BMAX], int P)
 {
     for (int stride = 1; stride < P; stride <<= 1) {
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b)
-            if (FULL || b < Bcur) acc[b] = __fadd_rn(acc[b], __shfl_xor_sync(0xffffffffu, acc[b], stride));
+        for (int b = 0; b < BMAX; ++b) acc[b] = __fadd_rn(acc[b], __shfl_xor_sync(0xffffffffu, acc[b], stride));
     }
 }
 
 // Scores of sample s (for the P lanes of its group) against all beams; handles D > 1024 through
 // a binary-counter pairwise combine of the 1024-dim slot totals (same tree as the oracle's).
-template <int BMAX, bool FULL, bool MULTISLOT>
+template <int BMAX, bool MULTISLOT>
 __device__ __forceinline__ void score_sample(const float* __restrict__ T, const float4* sa4, const float4* A4,
                                              const float4* E4, const float4* M4, const float4* beams4,
                                              const BeamGeom& g, int lg, const TfStream& st, uint64_t s,
-                                             const uint32_t (&h)[BMAX], int Bcur, float (&acc)[BMAX])
+                                             const BeamHash (&h)[BMAX], float (&acc)[BMAX])
 {
     const int bstride4 = g.DP >> 2;
     if (!MULTISLOT) {
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
         // lanes with lg >= nch only see zero padding (A = E = sa = M = beam = 0): contributes +0
-        score_chunk<BMAX, FULL>(T, sa4, A4, E4, M4, beams4, bstride4, g.P, lg, st,
-                                s * (uint64_t)g.D + (uint64_t)(32 * lg), h, Bcur, acc);
-        group_tree_sum<BMAX, FULL>(acc, g.P, Bcur);
+        score_chunk<BMAX>(T, sa4, A4, E4, M4, beams4, bstride4, g.P, lg, st,
+                          s * (uint64_t)g.D + (uint64_t)(32 * lg), h, acc);
+        group_tree_sum<BMAX>(acc, g.P);
     } else {
         float stack[12][BMAX];              // local memory; only for D > 1024 (up to 2^22 dims)
         for (int m = 0; m < g.nslots; ++m) {
 #pragma unroll
             for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
-            score_chunk<BMAX, FULL>(T, sa4, A4, E4, M4, beams4, bstride4, 32, m * 256 + lg, st,
-                                    s * (uint64_t)g.D + (uint64_t)(1024 * m + 32 * lg), h, Bcur, acc);
-            group_tree_sum<BMAX, FULL>(acc, 32, Bcur);
+            score_chunk<BMAX>(T, sa4, A4, E4, M4, beams4, bstride4, 32, m * 256 + lg, st,
+                              s * (uint64_t)g.D + (uint64_t)(1024 * m + 32 * lg), h, acc);
+            group_tree_sum<BMAX>(acc, 32);
             int lvl = 0;
             while ((m >> lvl) & 1) {
 #pragma unroll

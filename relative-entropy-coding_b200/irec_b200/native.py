@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libirec.so")
+LIB_PATH = os.environ.get("IREC_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libirec.so")
 
 IREC_OK = 0
 BLK_OK, BLK_BAD_KL, BLK_TOO_LONG = 0, 1, 2
