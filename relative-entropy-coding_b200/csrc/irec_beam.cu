@@ -12,6 +12,7 @@
 //                          candidate ranges (large S, large D, multi-GPU candidate sharding)
 #include "irec_beam.cuh"
 #include "irec_host.h"
+#include <string.h>
 
 // =============================================================================================
 // per-dim schedule of partition t (beam_search_coder.py:64-77,108-109; coder.py:141-154)
@@ -374,6 +375,8 @@ __global__ void __launch_bounds__(resident_max_threads<BMAX>(), 1) k_beam_encode
         }
     }
 }
+
+#include "irec_resident2.cuh"
 
 // =============================================================================================
 // K1b / K5: general path -- one partition per launch, candidates spread over the grid
@@ -795,6 +798,73 @@ static void launch_resident(const ResidentPlan& p, const ResidentArgs& a, cudaSt
     }
 }
 
+// ---- second-generation resident kernel (irec_resident2.cuh) ----
+static int resident_choice()
+{
+    // IREC_RESIDENT=1 forces the first-generation kernel, =2 the second (tests / A-B runs); default: 2 if it fits
+    const char* e = getenv("IREC_RESIDENT");
+    if (e && e[0] == '1') return 1;
+    if (e && e[0] == '2') return 2;
+    return 0;
+}
+
+template <int BMAX>
+static ResidentPlan plan_resident2_t(int nb, int max_D, int S, int B)
+{
+    ResidentPlan p{};
+    p.ok = false; p.bmax = BMAX;
+    if (max_D > 1024 || (int64_t)S * BMAX > 32768) return p;
+    const BeamGeom g = make_geom(max_D);
+    p.DPmax = g.DP;
+    p.NC = ((S * BMAX + 31) / 32) * 32;
+    p.smem = r2_smem_bytes<BMAX>(p.DPmax, p.NC);
+    const IrecDevice& dev = irec_device();
+    if (p.smem > (size_t)dev.max_smem_optin) return p;
+    // sample groups per warp layer: fewest layers with at most 12 warps, then the fewest warps for that
+    const int nsg = (S + g.SPW - 1) / g.SPW;
+    const int maxw = R2_THREADS / 32;
+    const int layers = (nsg + maxw - 1) / maxw;
+    int nw = (nsg + layers - 1) / layers;
+    if (nw < 8) nw = 8;                           // keep enough threads for the elementwise phases
+    if (nw > maxw) nw = maxw;
+    p.nthreads = nw * 32;
+    if (cudaFuncSetAttribute(k_beam_encode_resident2<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+        return p;
+    p.grid = std::min(nb, dev.sm_count);
+    p.ok = true;
+    return p;
+}
+
+static ResidentPlan plan_resident2(int nb, int max_D, int S, int B)
+{
+    switch (pick_bmax(B)) {
+        case 1: return plan_resident2_t<1>(nb, max_D, S, B);
+        case 2: return plan_resident2_t<2>(nb, max_D, S, B);
+        case 4: return plan_resident2_t<4>(nb, max_D, S, B);
+        case 8: return plan_resident2_t<8>(nb, max_D, S, B);
+        case 10: return plan_resident2_t<10>(nb, max_D, S, B);
+        case 16: return plan_resident2_t<16>(nb, max_D, S, B);
+        case 20: return plan_resident2_t<20>(nb, max_D, S, B);
+        case 32: return plan_resident2_t<32>(nb, max_D, S, B);
+    }
+    ResidentPlan p{}; p.ok = false; return p;
+}
+
+static void launch_resident2(const ResidentPlan& p, const Resident2Args& a, cudaStream_t s)
+{
+    switch (p.bmax) {
+        case 1: k_beam_encode_resident2<1><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 2: k_beam_encode_resident2<2><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 4: k_beam_encode_resident2<4><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 8: k_beam_encode_resident2<8><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 10: k_beam_encode_resident2<10><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 16: k_beam_encode_resident2<16><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 20: k_beam_encode_resident2<20><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+        case 32: k_beam_encode_resident2<32><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
+    }
+    irec_count_launch();
+}
+
 // ---- general path helpers ----
 #define GP_THREADS 256
 static size_t gp_score_smem(int cand_cap)
@@ -1043,6 +1113,25 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
         return irec_fail(IREC_E_CAPACITY, "beam_encode: workspace too small");
     if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "beam_encode: kl_per_partition must be > 0");
 
+    const int rchoice = resident_choice();
+    if (!irec_force_general() && rchoice != 1) {
+        const ResidentPlan plan2 = plan_resident2(nb, (int)max_block_dim, S, B);
+        if (plan2.ok) {
+            int* counter = reinterpret_cast<int*>(workspace);
+            if (cudaMemsetAsync(counter, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+            Resident2Args a;
+            a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
+            a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
+            a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
+            a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
+            a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
+            a.hist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+            a.work_counter = counter; a.DPmax = plan2.DPmax; a.NC = plan2.NC;
+            launch_resident2(plan2, a, s);
+            return irec_check_launch("k_beam_encode_resident2");
+        }
+        if (rchoice == 2) return irec_fail(IREC_E_CAPACITY, "beam_encode: IREC_RESIDENT=2 but the sizes do not fit the resident2 kernel");
+    }
     const ResidentPlan plan = irec_force_general() ? ResidentPlan{} : plan_resident(nb, (int)max_block_dim, S, B);
     if (plan.ok) {
         int* counter = reinterpret_cast<int*>(workspace);

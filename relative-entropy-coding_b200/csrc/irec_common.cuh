@@ -9,6 +9,8 @@
 
 #define IREC_PRIME 10007u
 #define IREC_CHUNK 32
+#define IREC_GEN 5u          // smallest primitive root of 10007
+#define IREC_ORD 10006u      // order of the multiplicative group
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (TF core/lib/random/philox_random.h).  One call = 4 consecutive stream elements.

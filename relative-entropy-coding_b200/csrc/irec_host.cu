@@ -157,6 +157,29 @@ int irec_init(void)
     dev.ratio_len = IREC_RATIO_LEN;
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return irec_fail(IREC_E_CUDA, "irec_init: table kernel failed");
+    // Exponent-indexed view of the same table.  10007 is prime and g = 5 generates Z_10007^*, so with
+    // a = dlog(r), c = dlog(h):  T[(r * h) mod 10007] = T2[a + c]  where T2[e] = T[g^(e mod 10006)];
+    // the modular product of beam_search_coder.py:45-47 becomes one integer add.  T2 holds the same
+    // float32 bit patterns as T (it is a permutation, stored twice so that a + c needs no wrap).
+    {
+        std::vector<float> T(10008), T2(IREC_T2_LEN, 0.f);
+        std::vector<uint16_t> dl4(10006);
+        if (cudaMemcpy(T.data(), dev.d_T, sizeof(float) * 10007, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return irec_fail(IREC_E_CUDA, "irec_init: table read-back failed");
+        uint32_t pw = 1;
+        for (int e = 0; e < 10006; ++e) {
+            T2[e] = T[pw];
+            if (e + 10006 < IREC_T2_LEN) T2[e + 10006] = T[pw];
+            dl4[pw - 1] = (uint16_t)(4 * e);
+            pw = (pw * IREC_GEN) % IREC_PRIME;
+        }
+        if (pw != 1) return irec_fail(IREC_E_INVALID, "irec_init: generator check failed");
+        if (cudaMalloc(&dev.d_T2, sizeof(float) * IREC_T2_LEN) != cudaSuccess ||
+            cudaMalloc(&dev.d_dl4, sizeof(uint16_t) * 10008) != cudaSuccess ||
+            cudaMemcpy(dev.d_T2, T2.data(), sizeof(float) * IREC_T2_LEN, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(dev.d_dl4, dl4.data(), sizeof(uint16_t) * 10006, cudaMemcpyHostToDevice) != cudaSuccess)
+            return irec_fail(IREC_E_CUDA, "irec_init: exponent table upload failed");
+    }
     dev.ready = true;
     g_dev[d] = dev;
     return IREC_OK;

@@ -1,0 +1,359 @@
+// irec_resident2.cuh -- K1a second generation: the persistent per-coder-block beam-search encoder.
+//
+// Reference loop being replaced: rec/coding/beam_search_coder.py:53-122 (one CTA = one coder-block, all
+// of its auxiliary variables); results are bit-identical to k_beam_encode_resident and to the oracle.
+//
+// What changed against the first kernel (profiles/r1_resident_v1_ncu.md: shared-memory wavefronts were
+// the top limiter -- 3.6-way conflicted quantile gathers + one beam float4 per 4 candidate-dims -- with
+// three IMADs per candidate-dim competing for the FMA pipe):
+//   * discrete-log addressing: 10007 is prime, g = 5 generates Z_10007^*, so with a = dlog(r) (per
+//     candidate sample and dim, shared by all beams) and c_b = dlog(h_b) (per beam, CTA-uniform)
+//         T[(r * h_b) mod 10007] = T2[a + c_b],   T2[e] = T[g^e]   (same float32 bit patterns)
+//     the modular product of beam_search_coder.py:45-47 is ONE integer add per candidate-dim;
+//   * every lane scores NS candidate samples of its 32-dim chunk at once, so a beam float4 read from
+//     shared memory serves 4 * NS candidate-dims instead of 4.
+// The float32 operation order of the canonical score (oracle/irec_oracle.c beam_score) is unchanged.
+#pragma once
+#include "irec_beam.cuh"
+
+#define R2_THREADS 384
+#define R2_TOPK_CAP 1024
+
+// byte offset (into T2) of stream word u:  4 * dlog(1 + u mod 10006)   (beam_search_coder.py:39-43)
+__device__ __forceinline__ uint32_t r2_exp4(const uint16_t* __restrict__ dl4, uint32_t u)
+{
+    return (uint32_t)dl4[u % IREC_ORD];
+}
+
+template <int BMAX>
+struct R2Group {   // beams per inner batch: G * 4 independent gathers in flight per candidate sample
+    static constexpr int G = (BMAX <= 5) ? BMAX : ((BMAX % 5 == 0) ? 5 : 4);
+};
+
+// Chunk sums of NS candidate samples against all BMAX beam slots.
+//   T2b   : s_T2 as bytes;  ad = 4 a;  cb4[b] = 4 c_b  (0 for unused slots; their sums are ignored)
+//   j_base[k] = s_k * D + first dim of the chunk;  q0 = float4 index of the chunk's first quad
+template <int BMAX, int NS>
+__device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, const uint16_t* __restrict__ dl4,
+                                               const uint32_t* __restrict__ cb4,
+                                               const float4* __restrict__ sa4, const float4* __restrict__ A4,
+                                               const float4* __restrict__ E4, const float4* __restrict__ M4,
+                                               const float4* __restrict__ beams4, int beam_stride4, int P, int q0,
+                                               const TfStream& st, const uint64_t (&j_base)[NS], float (&acc)[NS][BMAX])
+{
+    constexpr int G = R2Group<BMAX>::G;
+#pragma unroll 1
+    for (int iq = 0; iq < 8; ++iq) {
+        uint32_t ad[NS][4];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint64_t j = j_base[k] + 4 * iq;
+            const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
+            ad[k][0] = r2_exp4(dl4, u.x); ad[k][1] = r2_exp4(dl4, u.y);
+            ad[k][2] = r2_exp4(dl4, u.z); ad[k][3] = r2_exp4(dl4, u.w);
+        }
+        const int qi = q0 + iq * P;
+        const float4 sa = sa4[qi], A = A4[qi], E = E4[qi], M = M4[qi];
+#pragma unroll
+        for (int b0 = 0; b0 < BMAX; b0 += G) {
+            float4 bm[G];
+            uint32_t cb[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                bm[g] = beams4[(b0 + g) * beam_stride4 + qi];
+                cb[g] = cb4[b0 + g];
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                float tv[G][4];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        tv[g][e] = *reinterpret_cast<const float*>(T2b + (ad[k][e] + cb[g]));
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float x, d, t, a = acc[k][b0 + g];
+                    x = __fadd_rn(bm[g].x, __fmul_rn(tv[g][0], sa.x));
+                    d = __fadd_rn(x, -M.x); t = __fmaf_rn(A.x, d, E.x); a = __fmaf_rn(t, d, a);
+                    x = __fadd_rn(bm[g].y, __fmul_rn(tv[g][1], sa.y));
+                    d = __fadd_rn(x, -M.y); t = __fmaf_rn(A.y, d, E.y); a = __fmaf_rn(t, d, a);
+                    x = __fadd_rn(bm[g].z, __fmul_rn(tv[g][2], sa.z));
+                    d = __fadd_rn(x, -M.z); t = __fmaf_rn(A.z, d, E.z); a = __fmaf_rn(t, d, a);
+                    x = __fadd_rn(bm[g].w, __fmul_rn(tv[g][3], sa.w));
+                    d = __fadd_rn(x, -M.w); t = __fmaf_rn(A.w, d, E.w); a = __fmaf_rn(t, d, a);
+                    acc[k][b0 + g] = a;
+                }
+            }
+        }
+    }
+}
+
+// one round of a warp: NS sample groups (group = the 32/P samples of one warp row), scores -> s_scores
+template <int BMAX, int NS>
+__device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* dl4, const uint32_t* cb4,
+                                               const float4* sa4, const float4* A4, const float4* E4, const float4* M4,
+                                               const float4* beams4, const BeamGeom& g, int lane, const TfStream& st,
+                                               int sg_first, int sg_stride, int S, int Bcur, float* s_scores)
+{
+    const int lg = lane & (g.P - 1);
+    int s[NS];
+    uint64_t jb[NS];
+    float acc[NS][BMAX];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        s[k] = (sg_first + k * sg_stride) * g.SPW + lane / g.P;
+        jb[k] = (uint64_t)min(s[k], S - 1) * (uint64_t)g.D + (uint64_t)(32 * lg);
+#pragma unroll
+        for (int b = 0; b < BMAX; ++b) acc[k][b] = 0.f;
+    }
+    r2_score_chunk<BMAX, NS>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, acc);
+    // canonical pairwise tree over the P chunk sums (xor butterfly, same order as group_tree_sum)
+    for (int stride = 1; stride < g.P; stride <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int b = 0; b < BMAX; ++b)
+                acc[k][b] = __fadd_rn(acc[k][b], __shfl_xor_sync(0xffffffffu, acc[k][b], stride));
+    }
+    if (lg == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            if (s[k] < S) {
+#pragma unroll
+                for (int b = 0; b < BMAX; ++b)
+                    if (b < Bcur) {
+                        const float v = acc[k][b];
+                        s_scores[s[k] * Bcur + b] = (v == v) ? v : __int_as_float(0xff800000);
+                    }
+            }
+        }
+    }
+}
+
+// all candidates of one partition: S samples x Bcur beams
+template <int BMAX>
+__device__ __forceinline__ void r2_score_partition(const char* T2b, const uint16_t* dl4, const uint32_t* cb4,
+                                                   const float4* sa4, const float4* A4, const float4* E4, const float4* M4,
+                                                   const float4* beams4, const BeamGeom& g, const TfStream& st, int S,
+                                                   int Bcur, float* s_scores)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nsg = (S + g.SPW - 1) / g.SPW;
+    int sg = 0;
+    // rounds of 3, then 2, then 1 sample groups per warp (all warps take the same branch)
+    while (nsg - sg > 2 * nwarps) {
+        if (sg + warp < nsg)   // groups beyond nsg are clamped inside (scores not stored)
+            r2_score_round<BMAX, 3>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+        sg += 3 * nwarps;
+    }
+    if (nsg - sg > nwarps) {
+        if (sg + warp < nsg)
+            r2_score_round<BMAX, 2>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+        sg += 2 * nwarps;
+    } else if (nsg - sg > 0) {
+        if (sg + warp < nsg)
+            r2_score_round<BMAX, 1>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+        sg += nwarps;
+    }
+}
+
+struct Resident2Args {
+    const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
+    const int64_t* gidx; const int64_t* offs; int nb;
+    float omega; int S; int B; int64_t seed;
+    int32_t* out_indices; int max_aux; int32_t* out_n_aux; int32_t* out_status; float* out_sample;
+    const float* T2; const uint16_t* dl4; const float* ratio_tab; int ratio_len;
+    int2* hist;            // [gridDim.x][max_aux][BMAX]
+    int* work_counter;     // dynamic block queue
+    int DPmax;             // padded dims capacity of the shared arrays (multiple of 32)
+    int NC;                // capacity of the score array (>= S * BMAX)
+};
+
+template <int BMAX>
+__host__ __device__ constexpr size_t r2_smem_bytes(int DPmax, int NC)
+{
+    return 32 * sizeof(double) + sizeof(float) * ((size_t)IREC_T2_LEN + (size_t)BMAX * DPmax + (size_t)8 * DPmax + NC + 512 + 32) +
+           sizeof(uint16_t) * 10008 + sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32) + 16;
+}
+
+template <int BMAX>
+__global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const Resident2Args a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int DPm = a.DPmax;
+
+    // ---- shared memory carve-up (every array 16-byte aligned) ----
+    double* s_kl = reinterpret_cast<double*>(smem_raw);                  // [32]
+    float* s_T2 = reinterpret_cast<float*>(s_kl + 32);                   // [IREC_T2_LEN]
+    float* s_beams = s_T2 + IREC_T2_LEN;                                 // [BMAX][DPm]
+    float* s_sa = s_beams + (size_t)BMAX * DPm;                          // [DPm] x 8
+    float* s_A = s_sa + DPm; float* s_E = s_A + DPm; float* s_M = s_E + DPm;
+    float* s_cv = s_M + DPm; float* s_tv = s_cv + DPm; float* s_dmu = s_tv + DPm; float* s_cum = s_dmu + DPm;
+    float* s_scores = s_cum + DPm;                                       // [NC]
+    float* s_gmax = s_scores + a.NC;                                     // [512]
+    float* s_wsc = s_gmax + 512;                                         // [32] winners' scores
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);             // [32] winners' flat ids
+    int32_t* s_list = s_wid + 32;                                        // [R2_TOPK_CAP]
+    int32_t* s_ctl = s_list + R2_TOPK_CAP;                               // [4]
+    int32_t* s_hsum = s_ctl + 4;                                         // [2][32]
+    int32_t* s_misc = s_hsum + 64;                                       // [4]
+    uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_misc + 4);            // [32] 4 * dlog(h_b)
+    uint16_t* s_dl4 = reinterpret_cast<uint16_t*>(s_cb + 32);            // [10008]
+
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.T2);
+        float4* dst = reinterpret_cast<float4*>(s_T2);
+        for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
+        const uint32_t* s2 = reinterpret_cast<const uint32_t*>(a.dl4);
+        uint32_t* d2 = reinterpret_cast<uint32_t*>(s_dl4);
+        for (int i = tid; i < 10006 / 2; i += nt) d2[i] = s2[i];
+    }
+    const char* T2b = reinterpret_cast<const char*>(s_T2);
+    int2* hist = a.hist + (size_t)blockIdx.x * a.max_aux * BMAX;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_misc[0] = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int blk = s_misc[0];
+        if (blk >= a.nb) break;
+        const int64_t off = a.offs[blk];
+        const int D = (int)(a.offs[blk + 1] - off);
+        const BeamGeom g = make_geom(D);
+
+        // ---- load + KL (coder.py:499-501) ----
+        for (int i = tid; i < g.DP; i += nt) {
+            s_cv[i] = 0.f; s_tv[i] = 0.f; s_dmu[i] = 0.f; s_cum[i] = 0.f;
+            s_sa[i] = 0.f; s_A[i] = 0.f; s_E[i] = 0.f; s_M[i] = 0.f;
+        }
+        for (int i = tid; i < BMAX * g.DP; i += nt) s_beams[i] = 0.f;   // rows use stride g.DP
+        __syncthreads();
+        for (int c = tid; c < g.nch; c += nt) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * c + 32);
+            for (int d = 32 * c; d < hi; ++d) {
+                const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
+                acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
+                const int ci = ci_index(d, g.P);
+                s_cv[ci] = __fmul_rn(ps, ps);
+                s_tv[ci] = __fmul_rn(ts, ts);
+                s_dmu[ci] = __fadd_rn(tl, -pl);
+            }
+            s_kl[c] = acc;
+        }
+        const double kld = block_tree_sum_f64(s_kl, g.nch);
+        const int n_aux = n_aux_from_kl((float)kld, a.omega);
+        int status = IREC_BLK_OK;
+        if (n_aux <= 0) status = IREC_BLK_BAD_KL;
+        else if (n_aux > a.max_aux || n_aux > a.ratio_len) status = IREC_BLK_TOO_LONG;
+        if (tid == 0) { a.out_n_aux[blk] = n_aux; a.out_status[blk] = status; }
+        if (status != IREC_BLK_OK) continue;
+
+        if (tid < 64) s_hsum[tid] = 0;
+        int Bcur = 1, hb = 0;                      // hb: which half of s_hsum is current
+        const float4* sa4 = reinterpret_cast<const float4*>(s_sa);
+        const float4* A4 = reinterpret_cast<const float4*>(s_A);
+        const float4* E4 = reinterpret_cast<const float4*>(s_E);
+        const float4* M4 = reinterpret_cast<const float4*>(s_M);
+        const float4* beams4 = reinterpret_cast<const float4*>(s_beams);
+
+        for (int t = 0; t < n_aux; ++t) {
+            // ---- schedule (beam_search_coder.py:64-77) + the beams' table offsets c_b = dlog(simple_hash) ----
+            const float ratio = a.ratio_tab[n_aux - 1 - t];
+            for (int i = tid; i < g.DP; i += nt) {
+                const float cv = s_cv[i];
+                if (cv != 0.f) {                   // padding stays zero
+                    const SchedOut o = beam_sched_dim(cv, s_tv[i], s_dmu[i], s_cum[i], ratio);
+                    s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; s_cum[i] = o.cum_next;
+                }
+            }
+            const int32_t* hs = s_hsum + 32 * hb;
+            if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)s_dl4[hash_from_sum(hs[tid]) - 1] : 0u;
+            __syncthreads();
+
+            // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102) ----
+            const TfStream st = tf_stream_seeded(a.seed + t, a.seed + t);
+            if (Bcur == 1)
+                r2_score_partition<1>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, a.S, 1, s_scores);
+            else
+                r2_score_partition<BMAX>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, a.S, Bcur, s_scores);
+            __syncthreads();
+
+            // ---- top-B (beam_search_coder.py:86-89,104-106) ----
+            const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl);
+
+            // ---- history + hash sums of the new beams (beam_search_coder.py:92-95) ----
+            int32_t* hs_new = s_hsum + 32 * (hb ^ 1);
+            if (tid < Kout) {
+                const int f = s_wid[tid];
+                const int sj = f / Bcur, bj = f - sj * Bcur;
+                hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
+                hs_new[tid] = hsum_extend(hs[bj], sj, t);
+            }
+
+            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j), in place, two phases ----
+            const int nq = g.DP >> 2;
+            const int Qr = max(1, (nt * UPD_MAX) / Kout);
+            for (int qa = 0; qa < nq; qa += Qr) {
+                const int ntask = min(Qr, nq - qa) * Kout;
+                float4 nv[UPD_MAX];
+#pragma unroll
+                for (int k = 0; k < UPD_MAX; ++k) {
+                    const int task = tid + k * nt;
+                    if (task < ntask) {
+                        const int qq = qa + task / Kout, j = task % Kout;
+                        const int iqd = qq / g.P, l = qq - iqd * g.P;      // physical quad -> first dim
+                        const int d0 = 32 * l + 4 * iqd;
+                        const int f = s_wid[j];
+                        const int sj = f / Bcur, bj = f - sj * Bcur;
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (d0 < D) {
+                            const uint32_t cb = s_cb[bj];
+                            const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                            const float4 sa = sa4[qq];
+                            const float4 ob = beams4[bj * nq + qq];
+                            o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.x) + cb), sa.x));
+                            o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.y) + cb), sa.y));
+                            o.z = __fadd_rn(ob.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.z) + cb), sa.z));
+                            o.w = __fadd_rn(ob.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.w) + cb), sa.w));
+                            // dims beyond D inside the last quad: sa = 0 there, so o stays the (zero) padding
+                        }
+                        nv[k] = o;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < UPD_MAX; ++k) {
+                    const int task = tid + k * nt;
+                    if (task < ntask) {
+                        const int qq = qa + task / Kout, j = task % Kout;
+                        reinterpret_cast<float4*>(s_beams)[j * nq + qq] = nv[k];
+                    }
+                }
+                __syncthreads();
+            }
+            Bcur = Kout;
+            hb ^= 1;
+        }
+
+        // ---- emit: indices of the best beam (trace the back-pointers) and its sample (:118-122) ----
+        __syncthreads();
+        if (tid == 0) {
+            int j = 0;
+            int32_t* oi = a.out_indices + (size_t)blk * a.max_aux;
+            for (int t = n_aux - 1; t >= 0; --t) {
+                const int2 e = hist[(size_t)t * BMAX + j];
+                oi[t] = e.x;
+                j = e.y;
+            }
+        }
+        for (int d = tid; d < D; d += nt) {
+            const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+            a.out_sample[gi] = __fadd_rn(s_beams[ci_index(d, g.P)], a.p_loc[gi]);
+        }
+    }
+}

@@ -106,10 +106,18 @@ def run_beam_case(cuda, recipe, D, data_seed, omega, extra, B, seed):
     assert np.array_equal(bits(dec.cpu().numpy().reshape(-1)), bits(odec))
 
 
+@pytest.mark.parametrize("kernel", ["resident2", "resident1"])
 @pytest.mark.parametrize("case", BEAM_CASES, ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES])
-def test_beam_resident_vs_oracle(cuda, case):
+def test_beam_resident_vs_oracle(cuda, case, kernel):
+    """both generations of the persistent per-block kernel (IREC_RESIDENT=1: k_beam_encode_resident,
+    default: k_beam_encode_resident2 with discrete-log table addressing) are bit-identical to the oracle"""
     os.environ.pop("IREC_FORCE_GENERAL", None)
-    run_beam_case(cuda, *case)
+    if kernel == "resident1":
+        os.environ["IREC_RESIDENT"] = "1"
+    try:
+        run_beam_case(cuda, *case)
+    finally:
+        os.environ.pop("IREC_RESIDENT", None)
 
 
 @pytest.mark.parametrize("case", BEAM_CASES[:9], ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES[:9]])
