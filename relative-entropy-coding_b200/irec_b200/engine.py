@@ -9,6 +9,7 @@ import ctypes as C
 import torch
 
 from . import native as N
+from . import sharding as SH
 
 
 class CodingError(Exception):
@@ -223,12 +224,8 @@ class ShardedBeamBlock:
         self.ws_bytes = int(lib.irec_beam_step_workspace_bytes(self.D, self.B))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         # one gather buffer: per rank B records (16 B each) followed by the count in the last record slot
-        self.local = torch.zeros((self.B + 1) * 4, dtype=torch.int32, device=self.device)
-        self.gathered = torch.zeros(self.world * (self.B + 1) * 4, dtype=torch.int32, device=self.device)
-        self.counts = torch.zeros(self.world, dtype=torch.int32, device=self.device)
-        per = (self.S + self.world - 1) // self.world
-        self.s_begin = min(self.S, self.rank * per)
-        self.s_end = min(self.S, self.s_begin + per)
+        self.local, self.gathered = SH.alloc_exchange(self.B, self.world, self.device)
+        self.s_begin, self.s_end = SH.candidate_range(self.S, self.rank, self.world)
 
     def init(self, t_loc, t_scale, p_loc, p_scale, seed):
         lib = N.lib()
@@ -251,15 +248,8 @@ class ShardedBeamBlock:
         cnt_ptr = C.c_void_p(self.local.data_ptr() + B * N.RECORD_BYTES)
         N.check(lib.irec_beam_step_score(N.ptr(self.state), self.D, B, t, self.s_begin, self.s_end, 1, rec_ptr, cnt_ptr,
                                          N.ptr(self.ws), self.ws_bytes, N.stream_ptr()), "irec_beam_step_score")
-        if self.world > 1:
-            self.dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-            g = self.gathered.view(self.world, (B + 1) * 4)
-            recs = g[:, :B * 4].contiguous()
-            self.counts.copy_(g[:, B * 4])
-        else:
-            recs = self.local[:B * 4]
-            self.counts.copy_(self.local[B * 4:B * 4 + 1])
-        N.check(lib.irec_beam_step_commit(N.ptr(self.state), self.D, B, t, N.ptr(recs), N.ptr(self.counts), self.world,
+        recs, counts = SH.exchange_records(self.local, self.gathered, B, self.world, self.dist, self.group)
+        N.check(lib.irec_beam_step_commit(N.ptr(self.state), self.D, B, t, N.ptr(recs), N.ptr(counts), self.world,
                                           N.ptr(self.ws), self.ws_bytes, N.stream_ptr()), "irec_beam_step_commit")
 
     def finish(self):

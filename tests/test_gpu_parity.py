@@ -323,3 +323,17 @@ def test_generic_sampler_plugin_loop(cuda):
     indices, sample = coder.encode(t, p, seed=42)
     dec = coder.decode(p, list(indices), seed=42)
     assert torch.allclose(dec, sample, atol=1e-5)
+
+
+def test_sharded_block_nccl_two_ranks(cuda):
+    """candidate-range sharding over 2 GPUs (NCCL all-gather of top-B records) == oracle; needs >= 2 GPUs"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "run_sharded_nccl.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sharded nccl ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
