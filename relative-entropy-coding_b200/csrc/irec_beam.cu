@@ -987,6 +987,7 @@ int irec_beam_state_query(const void* state, int32_t* n_aux, int32_t* status, fl
 
 size_t irec_beam_step_workspace_bytes(int D, int B)
 {
+    if (irec_init() != IREC_OK) return 0;     // the size depends on the device's SM count
     const int grid_max = irec_device().sm_count * 4;
     return sizeof(irec_record_t) * ((size_t)grid_max * 32 + 32) + sizeof(int32_t) * ((size_t)grid_max + 8) +
            (sizeof(float) + sizeof(int32_t)) * ((size_t)grid_max * 32 + 64) + 256;
