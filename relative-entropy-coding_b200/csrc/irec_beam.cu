@@ -799,6 +799,21 @@ static void launch_resident(const ResidentPlan& p, const ResidentArgs& a, cudaSt
 }
 
 // ---- second-generation resident kernel (irec_resident2.cuh) ----
+// workspace: [0,256) block-queue counter | [256,512) R2Plan | back-pointer history | exponent table
+#define R2_TABLE_MAX_BYTES ((size_t)1 << 30)
+static size_t r2_ws_hist_bytes(int bmax, int max_aux)
+{
+    const size_t h = 512 + sizeof(int2) * (size_t)irec_device().sm_count * (size_t)max_aux * bmax;
+    return (h + 255) / 256 * 256;
+}
+static size_t r2_table_bytes(int max_D, int S, int max_aux)
+{
+    if (max_D > 1024) return 0;
+    const BeamGeom g = make_geom(max_D);
+    const size_t b = sizeof(uint2) * (size_t)R2_MAX_SIZES * (size_t)max_aux * (size_t)S * (size_t)(g.DP >> 2);
+    return b <= R2_TABLE_MAX_BYTES ? b : 0;       // very large S * max_aux: exponents are generated in place instead
+}
+
 static int resident_choice()
 {
     // IREC_RESIDENT=1 forces the first-generation kernel, =2 the second (tests / A-B runs); default: 2 if it fits
@@ -806,6 +821,12 @@ static int resident_choice()
     if (e && e[0] == '1') return 1;
     if (e && e[0] == '2') return 2;
     return 0;
+}
+
+static bool r2_no_table()
+{
+    const char* e = getenv("IREC_R2_NO_TABLE");      // tests: force the in-place Philox exponent path
+    return e && e[0] == '1';
 }
 
 template <int BMAX>
@@ -835,15 +856,19 @@ static ResidentPlan plan_resident2_t(int nb, int max_D, int S, int B)
     return p;
 }
 
+static int pick_bmax2(int B)
+{
+    const int opts[] = { 1, 4, 10, 20, 32 };       // fewer instantiations than the first kernel (compile time)
+    for (int o : opts) if (B <= o) return o;
+    return -1;
+}
+
 static ResidentPlan plan_resident2(int nb, int max_D, int S, int B)
 {
-    switch (pick_bmax(B)) {
+    switch (pick_bmax2(B)) {
         case 1: return plan_resident2_t<1>(nb, max_D, S, B);
-        case 2: return plan_resident2_t<2>(nb, max_D, S, B);
         case 4: return plan_resident2_t<4>(nb, max_D, S, B);
-        case 8: return plan_resident2_t<8>(nb, max_D, S, B);
         case 10: return plan_resident2_t<10>(nb, max_D, S, B);
-        case 16: return plan_resident2_t<16>(nb, max_D, S, B);
         case 20: return plan_resident2_t<20>(nb, max_D, S, B);
         case 32: return plan_resident2_t<32>(nb, max_D, S, B);
     }
@@ -854,11 +879,8 @@ static void launch_resident2(const ResidentPlan& p, const Resident2Args& a, cuda
 {
     switch (p.bmax) {
         case 1: k_beam_encode_resident2<1><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
-        case 2: k_beam_encode_resident2<2><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
         case 4: k_beam_encode_resident2<4><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
-        case 8: k_beam_encode_resident2<8><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
         case 10: k_beam_encode_resident2<10><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
-        case 16: k_beam_encode_resident2<16><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
         case 20: k_beam_encode_resident2<20><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
         case 32: k_beam_encode_resident2<32><<<p.grid, p.nthreads, p.smem, s>>>(a); break;
     }
@@ -1091,7 +1113,7 @@ size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, in
 {
     if (irec_init() != IREC_OK) return 0;
     const int bmax = pick_bmax(B) > 0 ? pick_bmax(B) : 32;
-    const size_t resident = sizeof(int2) * (size_t)irec_device().sm_count * (size_t)max_aux * bmax + 256;
+    const size_t resident = r2_ws_hist_bytes(bmax, max_aux) + r2_table_bytes((int)max_block_dim, S, max_aux);
     const size_t general = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256 + sizeof(irec_record_t) * 32 + 256 +
                            irec_beam_step_workspace_bytes((int)max_block_dim, B);
     (void)nb; (void)S;
@@ -1126,8 +1148,24 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
             a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
             a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
-            a.hist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+            unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+            a.hist = reinterpret_cast<int2*>(w + 512);
             a.work_counter = counter; a.DPmax = plan2.DPmax; a.NC = plan2.NC;
+            a.plan = nullptr; a.tab = nullptr;
+            const size_t tab_bytes = r2_table_bytes((int)max_block_dim, S, max_aux);
+            if (tab_bytes && !r2_no_table()) {
+                // exponent table of this launch (the candidate stream is the same for every coder-block)
+                R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
+                uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux));
+                if (cudaMemsetAsync(dplan, 0, sizeof(R2Plan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+                k_r2_plan<<<1, 256, 0, s>>>(block_offsets, nb, dplan);
+                irec_count_launch();
+                const int64_t items = (int64_t)(tab_bytes / sizeof(uint2));
+                const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)irec_device().sm_count * 16);
+                k_r2_exps<<<grid, 256, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, plan2.DPmax >> 2, tab);
+                irec_count_launch();
+                a.plan = dplan; a.tab = tab;
+            }
             launch_resident2(plan2, a, s);
             return irec_check_launch("k_beam_encode_resident2");
         }

@@ -33,24 +33,45 @@ struct R2Group {   // beams per inner batch: G * 4 independent gathers in flight
 // Chunk sums of NS candidate samples against all BMAX beam slots.
 //   T2b   : s_T2 as bytes;  ad = 4 a;  cb4[b] = 4 c_b  (0 for unused slots; their sums are ignored)
 //   j_base[k] = s_k * D + first dim of the chunk;  q0 = float4 index of the chunk's first quad
-template <int BMAX, int NS>
+//   row[k]: sample s_k's row of the precomputed exponent table (4 x uint16 per quad, CI layout) or nullptr
+//           (then the exponents come from Philox + dl4 in place)
+template <int BMAX, int NS, bool TAB>
 __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, const uint16_t* __restrict__ dl4,
                                                const uint32_t* __restrict__ cb4,
                                                const float4* __restrict__ sa4, const float4* __restrict__ A4,
                                                const float4* __restrict__ E4, const float4* __restrict__ M4,
                                                const float4* __restrict__ beams4, int beam_stride4, int P, int q0,
-                                               const TfStream& st, const uint64_t (&j_base)[NS], float (&acc)[NS][BMAX])
+                                               const TfStream& st, const uint64_t (&j_base)[NS],
+                                               const uint2* __restrict__ tab_t, const uint32_t (&row)[NS],
+                                               float (&acc)[NS][BMAX])
 {
     constexpr int G = R2Group<BMAX>::G;
+    uint2 nxt[NS];
+    if (TAB) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) nxt[k] = __ldg(tab_t + row[k]);
+    }
 #pragma unroll 1
     for (int iq = 0; iq < 8; ++iq) {
         uint32_t ad[NS][4];
+        if (TAB) {
 #pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            const uint64_t j = j_base[k] + 4 * iq;
-            const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
-            ad[k][0] = r2_exp4(dl4, u.x); ad[k][1] = r2_exp4(dl4, u.y);
-            ad[k][2] = r2_exp4(dl4, u.z); ad[k][3] = r2_exp4(dl4, u.w);
+            for (int k = 0; k < NS; ++k) {
+                const uint2 c = nxt[k];
+                ad[k][0] = c.x & 0xffffu; ad[k][1] = c.x >> 16; ad[k][2] = c.y & 0xffffu; ad[k][3] = c.y >> 16;
+            }
+            if (iq < 7) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) nxt[k] = __ldg(tab_t + row[k] + (iq + 1) * P);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const uint64_t j = j_base[k] + 4 * iq;
+                const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
+                ad[k][0] = r2_exp4(dl4, u.x); ad[k][1] = r2_exp4(dl4, u.y);
+                ad[k][2] = r2_exp4(dl4, u.z); ad[k][3] = r2_exp4(dl4, u.w);
+            }
         }
         const int qi = q0 + iq * P;
         const float4 sa = sa4[qi], A = A4[qi], E = E4[qi], M = M4[qi];
@@ -91,24 +112,29 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
 }
 
 // one round of a warp: NS sample groups (group = the 32/P samples of one warp row), scores -> s_scores
-template <int BMAX, int NS>
+// tab_t: exponent table of this block size and partition ([S][row_stride] uint2) or nullptr
+template <int BMAX, int NS, bool TAB>
 __device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* dl4, const uint32_t* cb4,
                                                const float4* sa4, const float4* A4, const float4* E4, const float4* M4,
                                                const float4* beams4, const BeamGeom& g, int lane, const TfStream& st,
+                                               const uint2* tab_t, int row_stride,
                                                int sg_first, int sg_stride, int S, int Bcur, float* s_scores)
 {
     const int lg = lane & (g.P - 1);
     int s[NS];
     uint64_t jb[NS];
+    uint32_t row[NS];                       // uint2 index of (sample row, first quad of the chunk) in tab_t
     float acc[NS][BMAX];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         s[k] = (sg_first + k * sg_stride) * g.SPW + lane / g.P;
-        jb[k] = (uint64_t)min(s[k], S - 1) * (uint64_t)g.D + (uint64_t)(32 * lg);
+        const int sc = min(s[k], S - 1);
+        jb[k] = TAB ? 0ull : (uint64_t)sc * (uint64_t)g.D + (uint64_t)(32 * lg);
+        row[k] = (uint32_t)(sc * row_stride + lg);
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) acc[k][b] = 0.f;
     }
-    r2_score_chunk<BMAX, NS>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, acc);
+    r2_score_chunk<BMAX, NS, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, tab_t, row, acc);
     // canonical pairwise tree over the P chunk sums (xor butterfly, same order as group_tree_sum)
     for (int stride = 1; stride < g.P; stride <<= 1) {
 #pragma unroll
@@ -133,11 +159,11 @@ __device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* 
 }
 
 // all candidates of one partition: S samples x Bcur beams
-template <int BMAX>
+template <int BMAX, bool TAB>
 __device__ __forceinline__ void r2_score_partition(const char* T2b, const uint16_t* dl4, const uint32_t* cb4,
                                                    const float4* sa4, const float4* A4, const float4* E4, const float4* M4,
-                                                   const float4* beams4, const BeamGeom& g, const TfStream& st, int S,
-                                                   int Bcur, float* s_scores)
+                                                   const float4* beams4, const BeamGeom& g, const TfStream& st,
+                                                   const uint2* tab_t, int row_stride, int S, int Bcur, float* s_scores)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nsg = (S + g.SPW - 1) / g.SPW;
@@ -145,17 +171,80 @@ __device__ __forceinline__ void r2_score_partition(const char* T2b, const uint16
     // rounds of 3, then 2, then 1 sample groups per warp (all warps take the same branch)
     while (nsg - sg > 2 * nwarps) {
         if (sg + warp < nsg)   // groups beyond nsg are clamped inside (scores not stored)
-            r2_score_round<BMAX, 3>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+            r2_score_round<BMAX, 3, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, tab_t, row_stride, sg + warp, nwarps, S, Bcur,
+                                      s_scores);
         sg += 3 * nwarps;
     }
     if (nsg - sg > nwarps) {
         if (sg + warp < nsg)
-            r2_score_round<BMAX, 2>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+            r2_score_round<BMAX, 2, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, tab_t, row_stride, sg + warp, nwarps, S, Bcur,
+                                      s_scores);
         sg += 2 * nwarps;
     } else if (nsg - sg > 0) {
         if (sg + warp < nsg)
-            r2_score_round<BMAX, 1>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, sg + warp, nwarps, S, Bcur, s_scores);
+            r2_score_round<BMAX, 1, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g, lane, st, tab_t, row_stride, sg + warp, nwarps, S, Bcur,
+                                      s_scores);
         sg += nwarps;
+    }
+}
+
+// Exponent table: per distinct block size D (at most R2_MAX_SIZES per launch), per auxiliary variable t < max_aux,
+// per candidate sample s: the byte offsets 4*dlog(r[s,d]) of all dims in CI layout, 4 x uint16 per quad.  r depends
+// on (seed + t, s, d, D) only (beam_search_coder.py:38-43: the same seed for every coder-block, coder.py:448), so the
+// Philox stream and its discrete logs are computed ONCE per launch instead of once per coder-block.
+#define R2_MAX_SIZES 2
+struct R2Plan {
+    int32_t n_sizes;               // distinct block sizes found (may exceed R2_MAX_SIZES: the rest uses in-place Philox)
+    int32_t D[R2_MAX_SIZES];
+    int32_t pad;
+};
+
+__global__ void k_r2_plan(const int64_t* __restrict__ offs, int nb, R2Plan* plan)
+{
+    // single CTA; plan was zeroed by the host (cudaMemsetAsync)
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int D = (int)(offs[b + 1] - offs[b]);
+        if (D <= 0) continue;
+        for (int k = 0; k < R2_MAX_SIZES; ++k) {
+            const int old = atomicCAS(&plan->D[k], 0, D);
+            if (old == 0 || old == D) break;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int k = 0; k < R2_MAX_SIZES; ++k) n += plan->D[k] != 0;
+        plan->n_sizes = n;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
+                                                 int64_t seed, int S, int max_aux, int row_stride, uint2* __restrict__ tab)
+{
+    // one thread per (size k, t, s, quad)
+    const int64_t per_size = (int64_t)max_aux * S * row_stride;
+    const int64_t total = per_size * R2_MAX_SIZES;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / per_size);
+        const int D = plan->D[k];
+        if (D == 0) continue;
+        int64_t r = i - (int64_t)k * per_size;
+        const int qq = (int)(r % row_stride); r /= row_stride;
+        const int s = (int)(r % S);
+        const int t = (int)(r / S);
+        const BeamGeom g = make_geom(D);
+        uint2 o = make_uint2(0u, 0u);
+        if (qq < (g.DP >> 2)) {
+            const int iqd = qq / g.P, l = qq - iqd * g.P;
+            const int d0 = 32 * l + 4 * iqd;
+            if (d0 < D) {
+                const TfStream st = tf_stream_seeded(seed + t, seed + t);
+                const uint4 u = tf_stream_quad_at(st, (uint64_t)s * (uint64_t)D + (uint64_t)d0);
+                o.x = (uint32_t)dl4[u.x % IREC_ORD] | ((uint32_t)dl4[u.y % IREC_ORD] << 16);
+                o.y = (uint32_t)dl4[u.z % IREC_ORD] | ((uint32_t)dl4[u.w % IREC_ORD] << 16);
+            }
+        }
+        tab[i] = o;
     }
 }
 
@@ -169,6 +258,8 @@ struct Resident2Args {
     int* work_counter;     // dynamic block queue
     int DPmax;             // padded dims capacity of the shared arrays (multiple of 32)
     int NC;                // capacity of the score array (>= S * BMAX)
+    const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
+    const uint2* tab;      // [R2_MAX_SIZES][max_aux][S][DPmax / 4]
 };
 
 template <int BMAX>
@@ -223,6 +314,13 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         const int64_t off = a.offs[blk];
         const int D = (int)(a.offs[blk + 1] - off);
         const BeamGeom g = make_geom(D);
+        const int row_stride = DPm >> 2;
+        const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
+        if (a.tab) {
+#pragma unroll
+            for (int k = 0; k < R2_MAX_SIZES; ++k)
+                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.max_aux * a.S * row_stride;
+        }
 
         // ---- load + KL (coder.py:499-501) ----
         for (int i = tid; i < g.DP; i += nt) {
@@ -277,10 +375,18 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
 
             // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102) ----
             const TfStream st = tf_stream_seeded(a.seed + t, a.seed + t);
-            if (Bcur == 1)
-                r2_score_partition<1>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, a.S, 1, s_scores);
-            else
-                r2_score_partition<BMAX>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, a.S, Bcur, s_scores);
+            const uint2* tab_t = tab_blk ? tab_blk + (size_t)t * a.S * row_stride : nullptr;
+            if (tab_t) {
+                if (Bcur == 1)
+                    r2_score_partition<1, true>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
+                else
+                    r2_score_partition<BMAX, true>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
+            } else {
+                if (Bcur == 1)
+                    r2_score_partition<1, false>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
+                else
+                    r2_score_partition<BMAX, false>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
+            }
             __syncthreads();
 
             // ---- top-B (beam_search_coder.py:86-89,104-106) ----
@@ -313,13 +419,20 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
                         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (d0 < D) {
                             const uint32_t cb = s_cb[bj];
-                            const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                            uint32_t e0, e1, e2, e3;
+                            if (tab_t) {
+                                const uint2 c = __ldg(tab_t + (size_t)sj * row_stride + qq);
+                                e0 = c.x & 0xffffu; e1 = c.x >> 16; e2 = c.y & 0xffffu; e3 = c.y >> 16;
+                            } else {
+                                const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                                e0 = r2_exp4(s_dl4, u.x); e1 = r2_exp4(s_dl4, u.y); e2 = r2_exp4(s_dl4, u.z); e3 = r2_exp4(s_dl4, u.w);
+                            }
                             const float4 sa = sa4[qq];
                             const float4 ob = beams4[bj * nq + qq];
-                            o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.x) + cb), sa.x));
-                            o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.y) + cb), sa.y));
-                            o.z = __fadd_rn(ob.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.z) + cb), sa.z));
-                            o.w = __fadd_rn(ob.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(s_dl4, u.w) + cb), sa.w));
+                            o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa.x));
+                            o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa.y));
+                            o.z = __fadd_rn(ob.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa.z));
+                            o.w = __fadd_rn(ob.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa.w));
                             // dims beyond D inside the last quad: sa = 0 there, so o stays the (zero) padding
                         }
                         nv[k] = o;

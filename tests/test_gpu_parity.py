@@ -106,7 +106,7 @@ def run_beam_case(cuda, recipe, D, data_seed, omega, extra, B, seed):
     assert np.array_equal(bits(dec.cpu().numpy().reshape(-1)), bits(odec))
 
 
-@pytest.mark.parametrize("kernel", ["resident2", "resident1"])
+@pytest.mark.parametrize("kernel", ["resident2", "resident2-notable", "resident1"])
 @pytest.mark.parametrize("case", BEAM_CASES, ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES])
 def test_beam_resident_vs_oracle(cuda, case, kernel):
     """both generations of the persistent per-block kernel (IREC_RESIDENT=1: k_beam_encode_resident,
@@ -114,10 +114,33 @@ def test_beam_resident_vs_oracle(cuda, case, kernel):
     os.environ.pop("IREC_FORCE_GENERAL", None)
     if kernel == "resident1":
         os.environ["IREC_RESIDENT"] = "1"
+    if kernel == "resident2-notable":
+        os.environ["IREC_R2_NO_TABLE"] = "1"      # exponents from Philox + dlog in place instead of the per-launch table
     try:
         run_beam_case(cuda, *case)
     finally:
         os.environ.pop("IREC_RESIDENT", None)
+        os.environ.pop("IREC_R2_NO_TABLE", None)
+
+
+def test_beam_ragged_blocks_one_launch(cuda):
+    """four different block sizes in ONE launch: two get a per-launch exponent table, the others generate their
+    candidate exponents in place; every block must equal the oracle on its own slice"""
+    import torch
+    from irec_b200 import engine
+    sizes = [100, 200, 37, 1000, 200, 100, 5]
+    n = sum(sizes)
+    tl, ts, pl, ps = synth.c2(n, data_seed=77)
+    d = to_dev((tl, ts, pl, ps), cuda)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    offsets = torch.as_tensor(offs, device=cuda)
+    res = engine.beam_encode_blocks(*d, None, offsets, len(sizes), max(sizes), 3.0, 36, 20, 42)
+    out = res.sample.cpu().numpy()
+    for b, D in enumerate(sizes):
+        lo, hi = offs[b], offs[b + 1]
+        ref = O.beam_encode_block(tl[lo:hi], ts[lo:hi], pl[lo:hi], ps[lo:hi], 3.0, 36, 20, 42)
+        assert res.indices[b] == ref["indices"].tolist(), (b, D)
+        assert np.array_equal(bits(out[lo:hi]), bits(ref["sample"])), (b, D)
 
 
 @pytest.mark.parametrize("case", BEAM_CASES[:9], ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES[:9]])
