@@ -160,7 +160,9 @@ int irec_init(void)
     // Exponent-indexed view of the same table.  10007 is prime and g = 5 generates Z_10007^*, so with
     // a = dlog(r), c = dlog(h):  T[(r * h) mod 10007] = T2[a + c]  where T2[e] = T[g^(e mod 10006)];
     // the modular product of beam_search_coder.py:45-47 becomes one integer add.  T2 holds the same
-    // float32 bit patterns as T (it is a permutation, stored twice so that a + c needs no wrap).
+    // float32 bit patterns as T.  It is a permutation, stored three times: a + c needs no wrap, and every
+    // value lives at two word offsets a and a + 10006 whose shared-memory banks differ by 22 -- the per-launch
+    // exponent table (k_r2_exps) picks per gather instruction the copy that keeps bank multiplicity at <= 2.
     {
         std::vector<float> T(10008), T2(IREC_T2_LEN, 0.f);
         std::vector<uint16_t> dl4(10006);
@@ -168,8 +170,7 @@ int irec_init(void)
             return irec_fail(IREC_E_CUDA, "irec_init: table read-back failed");
         uint32_t pw = 1;
         for (int e = 0; e < 10006; ++e) {
-            T2[e] = T[pw];
-            if (e + 10006 < IREC_T2_LEN) T2[e + 10006] = T[pw];
+            for (int rep = 0; rep < 3; ++rep) T2[e + 10006 * rep] = T[pw];
             dl4[pw - 1] = (uint16_t)(4 * e);
             pw = (pw * IREC_GEN) % IREC_PRIME;
         }

@@ -9,7 +9,7 @@
 #include "../../include/irec.h"
 
 #define IREC_RATIO_LEN 65536
-#define IREC_T2_LEN 20012      // 2 * 10006 entries (index a + c <= 20010), padded to a multiple of 4
+#define IREC_T2_LEN 30020      // 3 * 10006 entries (index a' + c <= 30016, a' in {a, a + 10006}), padded to a multiple of 4
 
 struct IrecDevice {
     bool ready;
@@ -19,7 +19,7 @@ struct IrecDevice {
     float* d_T;        // [10008] quantile table, entry 0 unused
     float* d_ratio;    // [IREC_RATIO_LEN] power-law auxiliary ratios
     int ratio_len;
-    float* d_T2;       // [IREC_T2_LEN] exponent-indexed doubled quantile table: T2[e] = T[g^e mod 10007]
+    float* d_T2;       // [IREC_T2_LEN] exponent-indexed quantile table, stored three times: T2[e] = T[g^(e mod 10006) mod 10007]
     uint16_t* d_dl4;   // [10006] dl4[m] = 4 * dlog_g(m + 1): byte offset into T2 of r = m + 1
 };
 

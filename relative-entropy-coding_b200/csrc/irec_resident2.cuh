@@ -12,6 +12,13 @@
 //     the modular product of beam_search_coder.py:45-47 is ONE integer add per candidate-dim;
 //   * every lane scores NS candidate samples of its 32-dim chunk at once, so a beam float4 read from
 //     shared memory serves 4 * NS candidate-dims instead of 4.
+//   * two-choice bank assignment: T2 is stored three times in shared memory, so the value of exponent a
+//     lives at word offsets a and a + 10006 (banks differ by 22).  The per-launch exponent table picks,
+//     for the 32 lanes of every gather instruction, the copy that keeps the bank multiplicity at <= 2
+//     (random banks: 3.5 wavefronts per gather; two choices: ~2.2).  The choice is the same for every
+//     beam because all lanes add the same c_b.  To make room for the 120 KB table the schedule inputs
+//     (sigma_p^2, sigma_t^2, delta mu, cumulative variance) live in a per-CTA global scratch and the
+//     discrete-log table is read from global memory (it is only needed for c_b and the no-table path).
 // The float32 operation order of the canonical score (oracle/irec_oracle.c beam_score) is unchanged.
 #pragma once
 #include "irec_beam.cuh"
@@ -22,7 +29,14 @@
 // byte offset (into T2) of stream word u:  4 * dlog(1 + u mod 10006)   (beam_search_coder.py:39-43)
 __device__ __forceinline__ uint32_t r2_exp4(const uint16_t* __restrict__ dl4, uint32_t u)
 {
-    return (uint32_t)dl4[u % IREC_ORD];
+    return (uint32_t)__ldg(dl4 + u % IREC_ORD);
+}
+
+// exponent-table entry: 4 x uint16 word offsets a' (a or a + 10006) -> byte offsets into T2
+__device__ __forceinline__ void r2_unpack(const uint2 c, uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3)
+{
+    e0 = (c.x << 2) & 0x3fffcu; e1 = (c.x >> 14) & 0x3fffcu;
+    e2 = (c.y << 2) & 0x3fffcu; e3 = (c.y >> 14) & 0x3fffcu;
 }
 
 template <int BMAX>
@@ -57,8 +71,7 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
         if (TAB) {
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                const uint2 c = nxt[k];
-                ad[k][0] = c.x & 0xffffu; ad[k][1] = c.x >> 16; ad[k][2] = c.y & 0xffffu; ad[k][3] = c.y >> 16;
+                r2_unpack(nxt[k], ad[k][0], ad[k][1], ad[k][2], ad[k][3]);
             }
             if (iq < 7) {
 #pragma unroll
@@ -218,33 +231,93 @@ __global__ void k_r2_plan(const int64_t* __restrict__ offs, int nb, R2Plan* plan
     }
 }
 
-__global__ void __launch_bounds__(256) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
+// One thread per gather family (size k, auxiliary variable t, sample group sg, quad-in-chunk iqd): the 32 lanes
+// (sample row r = lane / P, chunk l = lane % P) of the four gather instructions e = 0..3 of that quad.  For each
+// instruction the lanes' word offsets a are assigned to copy 0 (a) or copy 1 (a + 10006) of T2 so that no bank
+// serves more than `cap` lanes: greedy "less loaded of the two banks", one-hop relocation when both are full,
+// cap raised from 2 only if that fails.  Any assignment yields the same values (T2[a] == T2[a + 10006]).
+#define R2_BANK_SHIFT (IREC_ORD & 31u)
+__global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
                                                  int64_t seed, int S, int max_aux, int row_stride, uint2* __restrict__ tab)
 {
-    // one thread per (size k, t, s, quad)
-    const int64_t per_size = (int64_t)max_aux * S * row_stride;
+    const int64_t per_size = (int64_t)max_aux * S * 8;
     const int64_t total = per_size * R2_MAX_SIZES;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i / per_size);
         const int D = plan->D[k];
         if (D == 0) continue;
         int64_t r = i - (int64_t)k * per_size;
-        const int qq = (int)(r % row_stride); r /= row_stride;
-        const int s = (int)(r % S);
+        const int iqd = (int)(r & 7); r >>= 3;
+        const int sg = (int)(r % S);
         const int t = (int)(r / S);
         const BeamGeom g = make_geom(D);
-        uint2 o = make_uint2(0u, 0u);
-        if (qq < (g.DP >> 2)) {
-            const int iqd = qq / g.P, l = qq - iqd * g.P;
-            const int d0 = 32 * l + 4 * iqd;
-            if (d0 < D) {
-                const TfStream st = tf_stream_seeded(seed + t, seed + t);
+        if (sg * g.SPW >= S) continue;
+        const TfStream st = tf_stream_seeded(seed + t, seed + t);
+        uint16_t av[4][32];
+        uint32_t live[4] = { 0u, 0u, 0u, 0u };     // lanes whose dim exists (the others read offset 0: one broadcast address)
+        for (int lane = 0; lane < 32; ++lane) {
+            const int row = lane / g.P, l = lane & (g.P - 1);
+            const int s = sg * g.SPW + row, d0 = 32 * l + 4 * iqd;
+            uint32_t e[4] = { 0u, 0u, 0u, 0u };
+            if (s < S && d0 < D) {
                 const uint4 u = tf_stream_quad_at(st, (uint64_t)s * (uint64_t)D + (uint64_t)d0);
-                o.x = (uint32_t)dl4[u.x % IREC_ORD] | ((uint32_t)dl4[u.y % IREC_ORD] << 16);
-                o.y = (uint32_t)dl4[u.z % IREC_ORD] | ((uint32_t)dl4[u.w % IREC_ORD] << 16);
+                e[0] = __ldg(dl4 + u.x % IREC_ORD) >> 2; e[1] = __ldg(dl4 + u.y % IREC_ORD) >> 2;
+                e[2] = __ldg(dl4 + u.z % IREC_ORD) >> 2; e[3] = __ldg(dl4 + u.w % IREC_ORD) >> 2;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (d0 + q < D) live[q] |= 1u << lane;
+                    else e[q] = 0u;
+                }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) av[q][lane] = (uint16_t)e[q];
         }
-        tab[i] = o;
+        uint32_t pick[4];                          // bit lane: use copy 1
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint32_t ch = 0u;
+            for (int cap = 2; cap <= 32; ++cap) {
+                unsigned char load[32];
+                for (int b = 0; b < 32; ++b) load[b] = 0;
+                ch = 0u;
+                bool ok = true;
+                for (int lane = 0; lane < 32 && ok; ++lane) {
+                    if (!((live[q] >> lane) & 1u)) continue;
+                    const uint32_t b0 = av[q][lane] & 31u, b1 = (b0 + R2_BANK_SHIFT) & 31u;
+                    const uint32_t c = load[b1] < load[b0] ? 1u : 0u;
+                    const uint32_t bank = c ? b1 : b0;
+                    if (load[bank] < cap) { load[bank]++; ch |= c << lane; continue; }
+                    bool placed = false;            // both banks full: move one earlier lane out of one of them
+                    for (uint32_t c2 = 0; c2 < 2 && !placed; ++c2) {
+                        const uint32_t bk = c2 ? b1 : b0;
+                        for (int j = 0; j < lane; ++j) {
+                            if (!((live[q] >> j) & 1u)) continue;
+                            const uint32_t j0 = av[q][j] & 31u, j1 = (j0 + R2_BANK_SHIFT) & 31u;
+                            const uint32_t cj = (ch >> j) & 1u;
+                            if ((cj ? j1 : j0) != bk) continue;
+                            const uint32_t alt = cj ? j0 : j1;
+                            if (load[alt] < cap) {
+                                load[alt]++; ch ^= 1u << j;          // j leaves bk, lane takes its place
+                                ch |= c2 << lane; placed = true; break;
+                            }
+                        }
+                    }
+                    ok = placed;
+                }
+                if (ok) break;
+            }
+            pick[q] = ch;
+        }
+        uint2* out = tab + (size_t)k * max_aux * S * row_stride + (size_t)t * S * row_stride;
+        for (int lane = 0; lane < 32; ++lane) {
+            const int row = lane / g.P, l = lane & (g.P - 1);
+            const int s = sg * g.SPW + row;
+            if (s >= S) continue;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = (uint32_t)av[q][lane] + (((pick[q] >> lane) & 1u) ? IREC_ORD : 0u);
+            out[(size_t)s * row_stride + iqd * g.P + l] = make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
+        }
     }
 }
 
@@ -258,6 +331,7 @@ struct Resident2Args {
     int* work_counter;     // dynamic block queue
     int DPmax;             // padded dims capacity of the shared arrays (multiple of 32)
     int NC;                // capacity of the score array (>= S * BMAX)
+    float* sched;          // [gridDim.x][4][DPmax] per-CTA scratch: sigma_p^2, sigma_t^2, delta mu, cumulative variance
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][max_aux][S][DPmax / 4]
 };
@@ -265,8 +339,8 @@ struct Resident2Args {
 template <int BMAX>
 __host__ __device__ constexpr size_t r2_smem_bytes(int DPmax, int NC)
 {
-    return 32 * sizeof(double) + sizeof(float) * ((size_t)IREC_T2_LEN + (size_t)BMAX * DPmax + (size_t)8 * DPmax + NC + 512 + 32) +
-           sizeof(uint16_t) * 10008 + sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32) + 16;
+    return 32 * sizeof(double) + sizeof(float) * ((size_t)IREC_T2_LEN + (size_t)BMAX * DPmax + (size_t)4 * DPmax + NC + 512 + 32) +
+           sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32) + 16;
 }
 
 template <int BMAX>
@@ -280,10 +354,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
     double* s_kl = reinterpret_cast<double*>(smem_raw);                  // [32]
     float* s_T2 = reinterpret_cast<float*>(s_kl + 32);                   // [IREC_T2_LEN]
     float* s_beams = s_T2 + IREC_T2_LEN;                                 // [BMAX][DPm]
-    float* s_sa = s_beams + (size_t)BMAX * DPm;                          // [DPm] x 8
+    float* s_sa = s_beams + (size_t)BMAX * DPm;                          // [DPm] x 4
     float* s_A = s_sa + DPm; float* s_E = s_A + DPm; float* s_M = s_E + DPm;
-    float* s_cv = s_M + DPm; float* s_tv = s_cv + DPm; float* s_dmu = s_tv + DPm; float* s_cum = s_dmu + DPm;
-    float* s_scores = s_cum + DPm;                                       // [NC]
+    float* s_scores = s_M + DPm;                                         // [NC]
+    float* g_cv = a.sched + (size_t)blockIdx.x * 4 * DPm;                // global scratch (this CTA only)
+    float* g_tv = g_cv + DPm; float* g_dmu = g_tv + DPm; float* g_cum = g_dmu + DPm;
     float* s_gmax = s_scores + a.NC;                                     // [512]
     float* s_wsc = s_gmax + 512;                                         // [32] winners' scores
     int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);             // [32] winners' flat ids
@@ -292,15 +367,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
     int32_t* s_hsum = s_ctl + 4;                                         // [2][32]
     int32_t* s_misc = s_hsum + 64;                                       // [4]
     uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_misc + 4);            // [32] 4 * dlog(h_b)
-    uint16_t* s_dl4 = reinterpret_cast<uint16_t*>(s_cb + 32);            // [10008]
 
     {
         const float4* src = reinterpret_cast<const float4*>(a.T2);
         float4* dst = reinterpret_cast<float4*>(s_T2);
         for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
-        const uint32_t* s2 = reinterpret_cast<const uint32_t*>(a.dl4);
-        uint32_t* d2 = reinterpret_cast<uint32_t*>(s_dl4);
-        for (int i = tid; i < 10006 / 2; i += nt) d2[i] = s2[i];
     }
     const char* T2b = reinterpret_cast<const char*>(s_T2);
     int2* hist = a.hist + (size_t)blockIdx.x * a.max_aux * BMAX;
@@ -324,7 +395,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
 
         // ---- load + KL (coder.py:499-501) ----
         for (int i = tid; i < g.DP; i += nt) {
-            s_cv[i] = 0.f; s_tv[i] = 0.f; s_dmu[i] = 0.f; s_cum[i] = 0.f;
+            g_cv[i] = 0.f; g_tv[i] = 0.f; g_dmu[i] = 0.f; g_cum[i] = 0.f;
             s_sa[i] = 0.f; s_A[i] = 0.f; s_E[i] = 0.f; s_M[i] = 0.f;
         }
         for (int i = tid; i < BMAX * g.DP; i += nt) s_beams[i] = 0.f;   // rows use stride g.DP
@@ -337,9 +408,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
                 const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
                 acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
                 const int ci = ci_index(d, g.P);
-                s_cv[ci] = __fmul_rn(ps, ps);
-                s_tv[ci] = __fmul_rn(ts, ts);
-                s_dmu[ci] = __fadd_rn(tl, -pl);
+                g_cv[ci] = __fmul_rn(ps, ps);
+                g_tv[ci] = __fmul_rn(ts, ts);
+                g_dmu[ci] = __fadd_rn(tl, -pl);
             }
             s_kl[c] = acc;
         }
@@ -363,14 +434,14 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
             // ---- schedule (beam_search_coder.py:64-77) + the beams' table offsets c_b = dlog(simple_hash) ----
             const float ratio = a.ratio_tab[n_aux - 1 - t];
             for (int i = tid; i < g.DP; i += nt) {
-                const float cv = s_cv[i];
+                const float cv = g_cv[i];
                 if (cv != 0.f) {                   // padding stays zero
-                    const SchedOut o = beam_sched_dim(cv, s_tv[i], s_dmu[i], s_cum[i], ratio);
-                    s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; s_cum[i] = o.cum_next;
+                    const SchedOut o = beam_sched_dim(cv, g_tv[i], g_dmu[i], g_cum[i], ratio);
+                    s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; g_cum[i] = o.cum_next;
                 }
             }
             const int32_t* hs = s_hsum + 32 * hb;
-            if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)s_dl4[hash_from_sum(hs[tid]) - 1] : 0u;
+            if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs[tid]) - 1)) : 0u;
             __syncthreads();
 
             // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102) ----
@@ -378,14 +449,14 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
             const uint2* tab_t = tab_blk ? tab_blk + (size_t)t * a.S * row_stride : nullptr;
             if (tab_t) {
                 if (Bcur == 1)
-                    r2_score_partition<1, true>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
+                    r2_score_partition<1, true>(T2b, a.dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
                 else
-                    r2_score_partition<BMAX, true>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
+                    r2_score_partition<BMAX, true>(T2b, a.dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
             } else {
                 if (Bcur == 1)
-                    r2_score_partition<1, false>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
+                    r2_score_partition<1, false>(T2b, a.dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, 1, s_scores);
                 else
-                    r2_score_partition<BMAX, false>(T2b, s_dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
+                    r2_score_partition<BMAX, false>(T2b, a.dl4, s_cb, sa4, A4, E4, M4, beams4, g, st, tab_t, row_stride, a.S, Bcur, s_scores);
             }
             __syncthreads();
 
@@ -421,11 +492,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
                             const uint32_t cb = s_cb[bj];
                             uint32_t e0, e1, e2, e3;
                             if (tab_t) {
-                                const uint2 c = __ldg(tab_t + (size_t)sj * row_stride + qq);
-                                e0 = c.x & 0xffffu; e1 = c.x >> 16; e2 = c.y & 0xffffu; e3 = c.y >> 16;
+                                r2_unpack(__ldg(tab_t + (size_t)sj * row_stride + qq), e0, e1, e2, e3);
                             } else {
                                 const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
-                                e0 = r2_exp4(s_dl4, u.x); e1 = r2_exp4(s_dl4, u.y); e2 = r2_exp4(s_dl4, u.z); e3 = r2_exp4(s_dl4, u.w);
+                                e0 = r2_exp4(a.dl4, u.x); e1 = r2_exp4(a.dl4, u.y); e2 = r2_exp4(a.dl4, u.z); e3 = r2_exp4(a.dl4, u.w);
                             }
                             const float4 sa = sa4[qq];
                             const float4 ob = beams4[bj * nq + qq];
