@@ -799,13 +799,14 @@ static void launch_resident(const ResidentPlan& p, const ResidentArgs& a, cudaSt
 }
 
 // ---- second-generation resident kernel (irec_resident2.cuh) ----
-// workspace: [0,256) block-queue counter | [256,512) R2Plan | back-pointer history | schedule scratch | exponent table
+// workspace: [0,256) block-queue counter | [256,512) R2Plan | back-pointer history | schedule scratch | block order | exponent table
 #define R2_TABLE_MAX_BYTES ((size_t)1 << 30)
 static size_t r2_ws_hist_bytes(int bmax, int max_aux)
 {
     const size_t h = 512 + sizeof(int2) * (size_t)irec_device().sm_count * (size_t)max_aux * bmax;
     return (h + 255) / 256 * 256;
 }
+static size_t r2_ws_order_bytes(int nb) { return ((size_t)nb * sizeof(int32_t) + 255) / 256 * 256; }
 static size_t r2_ws_sched_bytes()
 {
     return sizeof(float) * 4 * 1024 * (size_t)irec_device().sm_count;      // [grid][4][DPmax <= 1024]
@@ -1117,10 +1118,11 @@ size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, in
 {
     if (irec_init() != IREC_OK) return 0;
     const int bmax = pick_bmax(B) > 0 ? pick_bmax(B) : 32;
-    const size_t resident = r2_ws_hist_bytes(bmax, max_aux) + r2_ws_sched_bytes() + r2_table_bytes((int)max_block_dim, S, max_aux);
+    const size_t resident = r2_ws_hist_bytes(bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb) +
+                            r2_table_bytes((int)max_block_dim, S, max_aux);
     const size_t general = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256 + sizeof(irec_record_t) * 32 + 256 +
                            irec_beam_step_workspace_bytes((int)max_block_dim, B);
-    (void)nb; (void)S;
+    (void)S;
     return std::max(resident, general);
 }
 
@@ -1157,14 +1159,17 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             a.sched = reinterpret_cast<float*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux));
             a.work_counter = counter; a.DPmax = plan2.DPmax; a.NC = plan2.NC;
             a.plan = nullptr; a.tab = nullptr;
+            // distinct block sizes + the queue order (largest blocks first)
+            R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
+            int32_t* order = reinterpret_cast<int32_t*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes());
+            if (cudaMemsetAsync(dplan, 0, sizeof(R2Plan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+            k_r2_plan<<<1, 1024, 0, s>>>(block_offsets, nb, dplan, order);
+            irec_count_launch();
+            a.order = order;
             const size_t tab_bytes = r2_table_bytes((int)max_block_dim, S, max_aux);
             if (tab_bytes && !r2_no_table()) {
                 // exponent table of this launch (the candidate stream is the same for every coder-block)
-                R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
-                uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes());
-                if (cudaMemsetAsync(dplan, 0, sizeof(R2Plan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
-                k_r2_plan<<<1, 256, 0, s>>>(block_offsets, nb, dplan);
-                irec_count_launch();
+                uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb));
                 const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;      // one thread per gather family
                 const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
                 k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, plan2.DPmax >> 2, tab);

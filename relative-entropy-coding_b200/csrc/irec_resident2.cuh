@@ -212,11 +212,19 @@ struct R2Plan {
     int32_t pad;
 };
 
-__global__ void k_r2_plan(const int64_t* __restrict__ offs, int nb, R2Plan* plan)
+// Also writes `order`: the coder-blocks sorted by decreasing size (counting sort), the sequence in which the
+// persistent CTAs draw them from the queue -- the short blocks of a tensor (its last, partial block) go last and
+// fill the tail of the launch instead of leaving SMs idle behind a full-size block.
+__global__ void __launch_bounds__(1024) k_r2_plan(const int64_t* __restrict__ offs, int nb, R2Plan* plan, int32_t* __restrict__ order)
 {
     // single CTA; plan was zeroed by the host (cudaMemsetAsync)
+    __shared__ int s_cnt[1025];
+    for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-        const int D = (int)(offs[b + 1] - offs[b]);
+        const int64_t D64 = offs[b + 1] - offs[b];
+        const int D = D64 < 0 ? 0 : (D64 > 1024 ? 1024 : (int)D64);
+        atomicAdd(&s_cnt[1024 - D], 1);            // bucket 0 = largest
         if (D <= 0) continue;
         for (int k = 0; k < R2_MAX_SIZES; ++k) {
             const int old = atomicCAS(&plan->D[k], 0, D);
@@ -228,6 +236,14 @@ __global__ void k_r2_plan(const int64_t* __restrict__ offs, int nb, R2Plan* plan
         int n = 0;
         for (int k = 0; k < R2_MAX_SIZES; ++k) n += plan->D[k] != 0;
         plan->n_sizes = n;
+        int run = 0;
+        for (int i = 0; i < 1025; ++i) { const int c = s_cnt[i]; s_cnt[i] = run; run += c; }   // exclusive prefix
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int64_t D64 = offs[b + 1] - offs[b];
+        const int D = D64 < 0 ? 0 : (D64 > 1024 ? 1024 : (int)D64);
+        order[atomicAdd(&s_cnt[1024 - D], 1)] = b;
     }
 }
 
@@ -392,6 +408,7 @@ struct Resident2Args {
     int DPmax;             // padded dims capacity of the shared arrays (multiple of 32)
     int NC;                // capacity of the score array (>= S * BMAX)
     float* sched;          // [gridDim.x][4][DPmax] per-CTA scratch: sigma_p^2, sigma_t^2, delta mu, cumulative variance
+    const int32_t* order;  // queue position -> coder-block (largest blocks first), or nullptr
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][max_aux][S][DPmax / 4]
 };
@@ -440,8 +457,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         __syncthreads();
         if (tid == 0) s_misc[0] = atomicAdd(a.work_counter, 1);
         __syncthreads();
-        const int blk = s_misc[0];
-        if (blk >= a.nb) break;
+        if (s_misc[0] >= a.nb) break;
+        const int blk = a.order ? a.order[s_misc[0]] : s_misc[0];
         const int64_t off = a.offs[blk];
         const int D = (int)(a.offs[blk + 1] - off);
         const BeamGeom g = make_geom(D);
