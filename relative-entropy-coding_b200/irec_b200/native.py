@@ -56,6 +56,13 @@ _SIGNATURES = {
                                  _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irec_is_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "irec_launch_count": (C.c_int64, []),
+    # include/irec_io.h -- host C++ (arithmetic coder + .rec container), no CUDA calls
+    "irec_ac_encode": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "irec_ac_decode": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "irec_rec_pack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "irec_rec_read_header": (C.c_int, [_vp, _i64, _vp]),
+    "irec_rec_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "irec_rec_write_file": (C.c_int, [C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
