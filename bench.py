@@ -11,8 +11,9 @@ level's sample in the real model), every launch coding 128 x 9 blocks.
   value  : candidates scored / s, inputs resident in HBM (CUDA events)
   e2e    : same through the public API (rec.coding.BeamSearchCoder.encode_batch) from pinned host buffers,
            host<->device copies and index read-back inside the timed region
-  roofline: INT32/FP32 issue rate of the dominant kernel (k_beam_encode_resident<20>), algorithmic
-           instructions per candidate-dim W = 10 + 24/B' 
+  roofline: INT32/FP32 issue rate of the dominant kernel (k_beam_encode_resident2<20>), algorithmic
+           instructions per candidate-dim W = 10 + 24/B' (SURVEY.md 8d); secondary: HBM bytes and the
+           shared-memory wavefront rate (the measured limiter of the hot loop, profiles/)
 
 `--impl reference` times the CPU port of the reference (the C oracle, all host threads) on a bounded sample.
 """
@@ -123,12 +124,17 @@ def cpu_port_sample(n_blocks, threads):
     return cand / dt, cd / dt, parts / dt, dt, res, jobs
 
 
+def cpu_sample_blocks(cores):
+    """bounded CPU sample: ~0.4 s of single-core work per coder-block -> 10-20 s per step on all cores"""
+    return int(min(1024, max(32 * cores, 64)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_blocks = min(512, max(4 * cores, 8))
+    n_blocks = cpu_sample_blocks(cores)
     vals = []
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_port_sample(n_blocks, cores)
@@ -258,6 +264,10 @@ def main():
         c, d_, p_, i_ = work_model(na_all[lvl], dims)
         cand += c; cd += d_; parts += p_; instr += i_
         per_level_instr.append(i_)
+    if os.environ.get("IREC_BENCH_DUMP") and rank == 0:      # per-level work of this run (used by profiles/make_bench_launch_json.py)
+        per_level = [work_model(na_all[lvl], dims) for lvl in range(LEVELS)]
+        json.dump({"images_per_gpu": n_img, "levels": [{"candidates": c, "candidate_dims": d_, "partitions": p_} for c, d_, p_, _ in per_level]},
+                  open(os.environ["IREC_BENCH_DUMP"], "w"))
     kernel_ms = np.array([a.elapsed_time(b) for a, b in kernel_events]).reshape(args.steps, LEVELS)
     kernel_ms_avg = float(kernel_ms.mean())
     achieved_instr = float(np.mean(per_level_instr)) / (kernel_ms_avg * 1e-3)
@@ -307,6 +317,18 @@ def main():
         peak_instr = sm_count * 128 * sm_max_mhz * 1e6
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes_level = float(16 * dims.sum() + 4 * dims.sum() + 4 * na_all.mean(axis=0).sum())
+        # measured per-launch DRAM traffic and shared-memory wavefronts per candidate-dim of the same launch shape,
+        # from the committed `ncu --set full` capture (profiles/r1_bench_launch_ncu.json)
+        traffic, traffic_src, wf_per_cd = None, None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_launch_ncu.json")))
+            if prof.get("images_per_gpu") == n_img:
+                traffic = float(prof["dram_bytes_read"] + prof["dram_bytes_write"])
+            wf_per_cd = float(prof["shared_wavefronts"]) / float(prof["candidate_dims"])
+            traffic_src = prof.get("source")
+        except Exception:
+            pass
+        smem_rate = (cd_all / world / sec) * wf_per_cd if wf_per_cd else float("nan")
         line = {
             "metric": METRIC, "value": cand_all / sec, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -319,18 +341,21 @@ def main():
             "clocks": clock_info,
             "e2e": {"value": cand_all / (e2e_ms * 1e-3), "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "roofline": {"bound": "issue", "kernel": "k_beam_encode_resident<20>", "achieved": achieved_instr / 1e9,
+            "roofline": {"bound": "issue", "kernel": "k_beam_encode_resident2<20>", "achieved": achieved_instr / 1e9,
                          "peak": peak_instr / 1e9, "unit": "G lane-instr/s", "frac": achieved_instr / peak_instr,
                          "peak_source": f"{sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
                          "work_model": "W = 10 + 24/B' lane-instr per candidate-dim (SURVEY.md 8d)",
-                         "avg_launch_ms": kernel_ms_avg, "traffic": None,
+                         "avg_launch_ms": kernel_ms_avg, "traffic": traffic, "traffic_source": traffic_src,
+                         "smem": {"wavefronts_per_candidate_dim": wf_per_cd, "achieved_gwf_s": smem_rate / 1e9,
+                                  "peak_gwf_s": sm_count * sm_max_mhz * 1e6 / 1e9,
+                                  "frac": smem_rate / (sm_count * sm_max_mhz * 1e6), "source": traffic_src},
                          "hbm": {"achieved_gbs": alg_bytes_level / (kernel_ms_avg * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "frac": alg_bytes_level / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_launch": alg_bytes_level}},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_blocks = min(512, max(4 * cores, 8))
+            n_blocks = cpu_sample_blocks(cores)
             v, cdv, pv, dt, res, jobs = cpu_port_sample(n_blocks, cores)
             line["cpu_baseline"] = {"value": v, "unit": "candidates/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_blocks} coder-blocks (D=1000, S=36, B=20) of the same workload, C oracle "

@@ -1,0 +1,94 @@
+"""End-to-end at BASELINE.json's full sizes (configs[1] and configs[2]) through the callers' flow
+(rec.models.LatentHierarchy = the compress/decompress loops of resnet_vae.py:803-860 and large_2_level_vae.py:406-456):
+coder.encode per level -> .rec file -> read back -> coder.decode per level.  Size-independent properties: the decoded
+latents are bit-identical to the encoder's, every level's prior depends on the previous level's decoded latent, the file
+round-trips the index lists, and bits/dim from the index stream equal n_aux * log2(S).  A sample of coder-blocks of every
+level is also checked against the CPU oracle on the very inputs the GPU coded."""
+import os
+
+import numpy as np
+import pytest
+
+import synth  # noqa: F401
+from oracle import oracle as O
+from oracle import ref_io
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def cuda(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda:0"
+
+
+def _oracle_spot_check(ladder, latents, level, coder, block_indices, seed, blocks):
+    """oracle encode of a few coder-blocks of `level`, fed with the exact posterior/prior the GPU saw"""
+    prior = ladder.prior(level, latents[:level])
+    post = ladder.posterior(level, latents[:level])
+    tl, ts = post.loc.cpu().numpy().reshape(-1), post.scale.cpu().numpy().reshape(-1)
+    pl, ps = prior.loc.cpu().numpy().reshape(-1), prior.scale.cpu().numpy().reshape(-1)
+    n, bs = tl.size, coder.block_size
+    perm = O.shuffle_perm(n, seed)
+    lat = latents[level].cpu().numpy().reshape(-1)
+    for b in blocks:
+        sel = perm[b * bs:min(n, (b + 1) * bs)]
+        ref = O.beam_encode_block(tl[sel], ts[sel], pl[sel], ps[sel], coder.kl_per_partition, coder.n_samples, coder.n_beams, seed)
+        assert block_indices[level][b] == ref["indices"].tolist(), (level, b)
+        assert np.array_equal(bits(lat[sel]), bits(ref["sample"])), (level, b)
+
+
+def _run(cuda, tmp_path, shapes, recipe, B, extra, image_shape, spot):
+    import torch
+    from rec.coding import BeamSearchCoder
+    from rec.models import LatentHierarchy, SyntheticLadder
+    seed = 42
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=B, extra_samples=extra, block_size=1000)
+    ladder = SyntheticLadder(shapes, recipe=recipe, data_seed=5, device=cuda)
+    model = LatentHierarchy(ladder)
+    path = str(tmp_path / "image.rec")
+    block_indices, latents = model.compress(seed, coder, file_path=path, image_shape=image_shape)
+    assert [len(t) for t in block_indices] == [-(-int(np.prod(s)) // 1000) for s in shapes]
+    # the file holds exactly the index lists; decode from the FILE only
+    decoded = model.decompress(coder, file_path=path)
+    for a, b in zip(latents, decoded):
+        assert a.shape == b.shape and torch.equal(a, b)
+    # bits/dim: codelength (nats) of the index stream == n_aux * ln S; the arithmetic-coded file stays close to it
+    n_idx = sum(len(b) for t in block_indices for b in t)
+    dims = sum(int(np.prod(s)) for s in shapes)
+    nats = model.get_codelength(block_indices, coder)
+    assert np.isclose(nats, n_idx * np.log(coder.n_samples), rtol=1e-12)
+    ideal_bits = nats / np.log(2)
+    file_bits = 8 * os.path.getsize(path)
+    assert ideal_bits <= file_bits <= 1.05 * ideal_bits + 8 * (28 + 16 * len(shapes)) + 64 * len(shapes) + 16 * sum(len(t) for t in block_indices)
+    for level, blocks in spot:
+        _oracle_spot_check(ladder, latents, level, coder, block_indices, seed, blocks)
+    # a corrupted index derails the decode (the ladder is really sequential)
+    bad = [[list(b) for b in t] for t in block_indices]
+    bad[0][0][0] = (bad[0][0][0] + 1) % coder.n_samples
+    wrong = model.decompress(coder, block_indices=bad, seed=seed)
+    assert not torch.equal(wrong[0], latents[0]) and not torch.equal(wrong[-1], latents[-1])
+    if ref_io.available():          # the reference's own reader accepts our file
+        back = ref_io.call([{"op": "rec_read", "path": path}])[0]
+        assert back["block_indices"] == block_indices and back["seed"] == seed and back["image_shape"] == list(image_shape)
+    return ideal_bits / dims, file_bits / dims
+
+
+def test_lossy_two_level_kodak_shape(cuda, tmp_path):
+    """configs[2]: large_level_2_vae latents for a 768x512 image: [8,12,128] then [32,48,196]; n_beams=10, extra_samples=1."""
+    ideal, actual = _run(cuda, tmp_path, [(8, 12, 128), (32, 48, 196)], "c3", 10, 1.0, (512, 768, 3),
+                         spot=[(0, [0, 12]), (1, [0, 150, 301])])
+    assert 0.1 < ideal < 20 and actual >= ideal
+
+
+def test_lossless_resnet_vae_cifar_shape(cuda, tmp_path):
+    """configs[1]: resnet_vae, 24 latent tensors [16,16,32] for a 32x32 image; n_beams=20, extra_samples=1.2"""
+    ideal, actual = _run(cuda, tmp_path, [(16, 16, 32)] * 24, "c2", 20, 1.2, (32, 32, 3),
+                         spot=[(0, [0, 8]), (11, [3]), (23, [8])])
+    assert 0.1 < ideal < 20 and actual >= ideal
