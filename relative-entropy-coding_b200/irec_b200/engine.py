@@ -49,6 +49,8 @@ def kl_naux(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega
 
 
 def _raise_status(status, n_aux, what):
+    if not bool((status != N.BLK_OK).any()):
+        return
     bad = (status != N.BLK_OK).nonzero()
     if bad.numel():
         b = int(bad[0])
@@ -94,20 +96,24 @@ def beam_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets
     packed = torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1).cpu()   # one D2H copy
     status, n_aux, idx = packed[:, 0], packed[:, 1], packed[:, 2:]
     _raise_status(status, n_aux, "beam encode")
-    indices = [idx[b, :int(n_aux[b])].tolist() for b in range(nb)]
+    idx_np, na_np = idx.numpy(), n_aux.numpy().tolist()          # numpy slicing: ~10x cheaper per block than tensor indexing
+    indices = [idx_np[b, :na_np[b]].tolist() for b in range(nb)]
     return BeamEncodeResult(indices, n_aux, out_sample, kl)
 
 
 def pack_indices(indices, dtype, device):
     nb = len(indices)
     max_aux = max(1, max(len(i) for i in indices))
-    host = torch.zeros((nb, max_aux), dtype=dtype)
-    n = torch.zeros(nb, dtype=torch.int32)
+    import numpy as np
+    np_dtype = np.int64 if dtype == torch.int64 else np.int32
+    host = np.zeros((nb, max_aux), dtype=np_dtype)
+    n = np.zeros(nb, dtype=np.int32)
     for b, ind in enumerate(indices):
-        n[b] = len(ind)
-        if len(ind):
-            host[b, :len(ind)] = torch.as_tensor([int(v) for v in ind], dtype=dtype)
-    return host.to(device), n.to(device), max_aux
+        k = len(ind)
+        n[b] = k
+        if k:
+            host[b, :k] = np.asarray([int(v) for v in ind], dtype=np_dtype)
+    return torch.from_numpy(host).to(device), torch.from_numpy(n).to(device), max_aux
 
 
 def beam_decode_blocks(p_loc, p_scale, gather_idx, block_offsets, nb, S, seed, indices):
@@ -147,7 +153,8 @@ def is_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, 
                                ws_bytes, N.stream_ptr()), "irec_is_encode")
     st_h, n_h, idx_h = out_st.cpu(), out_n.cpu(), out_idx.cpu()
     _raise_status(st_h, n_h, "importance encode")
-    indices = [idx_h[b, :int(n_h[b])].tolist() for b in range(nb)]
+    idx_np, n_np = idx_h.numpy(), n_h.numpy().tolist()
+    indices = [idx_np[b, :n_np[b]].tolist() for b in range(nb)]
     return indices, out_sample
 
 
