@@ -337,10 +337,11 @@ __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan
     }
 }
 
-// Winners' new beams, in place.  One thread owns one half quad column (2 dims) of the beam matrix: it reads the
-// parents of all winners for its dims into registers, then overwrites the column -- no barrier, no cross-thread
-// hazard.  s_list[j] = s_j, s_list[32 + j] = b_j.  Kept out of line so that it does not disturb the register
-// allocation of the scoring loop.
+// Winners' new beams, in place (beam_search_coder.py:92-93): beam_j <- beam_{b_j} + a(s_j, b_j).
+// One WARP per winner j (s_list[j] = s_j, s_list[32 + j] = b_j), lanes stride over the quad columns: the winner's
+// exponent row is one coalesced 8-byte load per lane and quad, all issued up front; the parent quad is a conflict-free
+// LDS.128.  Every new value is held in registers until a CTA barrier, then stored -- a parent may be another winner's
+// destination.  Kept out of line so that it does not disturb the register allocation of the scoring loop.
 template <int BMAX>
 __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __restrict__ dl4, int off_cb, int off_list,
                                               int off_sa, int off_beams, int DP, int P,
@@ -350,50 +351,63 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
     const char* T2b = reinterpret_cast<const char*>(smem_raw + off_T2);
     const uint32_t* s_cb = reinterpret_cast<const uint32_t*>(smem_raw + off_cb);
     const int32_t* s_list = reinterpret_cast<const int32_t*>(smem_raw + off_list);
-    const float* s_sa = reinterpret_cast<const float*>(smem_raw + off_sa);
-    float* s_beams = reinterpret_cast<float*>(smem_raw + off_beams);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int nq = DP >> 2, lgP = __ffs(P) - 1;                 // P is a power of two
-    const float2* sa2 = reinterpret_cast<const float2*>(s_sa);
-    float2* beams2 = reinterpret_cast<float2*>(s_beams);
-    for (int task = tid; task < 2 * nq; task += nt) {              // task = (quad column, which half of it)
-        const int qq = task >> 1, hf = task & 1;
-        const int iqd = qq >> lgP, l = qq & (P - 1);             // physical quad -> first dim
-        const int d0 = 32 * l + 4 * iqd + 2 * hf;
-        if (d0 >= D) continue;                                     // pure padding: stays zero
-        const float2 sa = sa2[task];
-        uint32_t cw[BMAX];                                         // packed exponents of (s_j, my 2 dims): all loads first
-        if (tab_t) {
-            const uint32_t* tw = reinterpret_cast<const uint32_t*>(tab_t + qq) + hf;
+    const float4* sa4 = reinterpret_cast<const float4*>(smem_raw + off_sa);
+    float4* beams4 = reinterpret_cast<float4*>(smem_raw + off_beams);
+    constexpr int WPW = (BMAX + 7) / 8;                             // winners per warp (the CTA has at least 8 warps)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nq = DP >> 2, lgP = __ffs(P) - 1;                     // P is a power of two; nq <= 256
+    float4 nv[WPW][8];
 #pragma unroll
-            for (int j = 0; j < BMAX; ++j) cw[j] = j < Kout ? __ldg(tw + 2 * (size_t)s_list[j] * row_stride) : 0u;
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < Kout; ++j) {
-                const uint4 u = tf_stream_quad_at(st, (uint64_t)s_list[j] * (uint64_t)D + (uint64_t)(d0 - 2 * hf));
-                const uint32_t w = (r2_exp4(dl4, hf ? u.z : u.x) >> 2) | ((r2_exp4(dl4, hf ? u.w : u.y) >> 2) << 16);
+    for (int w = 0; w < WPW; ++w) {
+        const int j = warp + w * nwarps;
+        if (j < Kout) {
+            const int sj = s_list[j], bj = s_list[32 + j];
+            const uint32_t cb = s_cb[bj];
+            uint2 ex[8];
+            if (tab_t) {
 #pragma unroll
-                for (int jj = 0; jj < BMAX; ++jj) if (jj == j) cw[jj] = w;
+                for (int i = 0; i < 8; ++i) {
+                    const int qq = lane + 32 * i;
+                    ex[i] = qq < nq ? __ldg(tab_t + (size_t)sj * row_stride + qq) : make_uint2(0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int qq = lane + 32 * i;
+                const int iqd = qq >> lgP, l = qq & (P - 1);        // physical quad -> first dim
+                const int d0 = 32 * l + 4 * iqd;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qq < nq && d0 < D) {
+                    uint32_t e0, e1, e2, e3;
+                    if (tab_t) {
+                        r2_unpack(ex[i], e0, e1, e2, e3);
+                    } else {
+                        const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                        e0 = r2_exp4(dl4, u.x); e1 = r2_exp4(dl4, u.y); e2 = r2_exp4(dl4, u.z); e3 = r2_exp4(dl4, u.w);
+                    }
+                    const float4 sa = sa4[qq];
+                    const float4 ob = beams4[bj * nq + qq];
+                    o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa.x));
+                    o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa.y));
+                    o.z = __fadd_rn(ob.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa.z));
+                    o.w = __fadd_rn(ob.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa.w));
+                    // dims beyond D inside the last quad: sa = 0 and the parent is 0 there, so the padding stays zero
+                }
+                nv[w][i] = o;
             }
         }
-        float2 nv[BMAX];
+    }
+    __syncthreads();
 #pragma unroll
-        for (int j = 0; j < BMAX; ++j) {
-            if (j < Kout) {
-                const int bj = s_list[32 + j];
-                const uint32_t cb = s_cb[bj];
-                const uint32_t e0 = (cw[j] << 2) & 0x3fffcu, e1 = (cw[j] >> 14) & 0x3fffcu;
-                const float2 ob = beams2[2 * (bj * nq + qq) + hf];
-                float2 o;
-                o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa.x));
-                o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa.y));
-                // a dim beyond D inside the last pair: sa = 0 and the parent is 0 there, so the padding stays zero
-                nv[j] = o;
+    for (int w = 0; w < WPW; ++w) {
+        const int j = warp + w * nwarps;
+        if (j < Kout) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int qq = lane + 32 * i;
+                if (qq < nq) beams4[j * nq + qq] = nv[w][i];      // pure padding columns receive zeros (they were zero)
             }
         }
-#pragma unroll
-        for (int j = 0; j < BMAX; ++j)
-            if (j < Kout) beams2[2 * (j * nq + qq) + hf] = nv[j];
     }
 }
 

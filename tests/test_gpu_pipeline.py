@@ -73,7 +73,8 @@ def _run(cuda, tmp_path, shapes, recipe, B, extra, image_shape, spot):
     bad = [[list(b) for b in t] for t in block_indices]
     bad[0][0][0] = (bad[0][0][0] + 1) % coder.n_samples
     wrong = model.decompress(coder, block_indices=bad, seed=seed)
-    assert not torch.equal(wrong[0], latents[0]) and not torch.equal(wrong[-1], latents[-1])
+    # (the synthetic coupling is a contraction, so the perturbation fades after a few levels: check the next one)
+    assert not torch.equal(wrong[0], latents[0]) and not torch.equal(wrong[1], latents[1])
     if ref_io.available():          # the reference's own reader accepts our file
         back = ref_io.call([{"op": "rec_read", "path": path}])[0]
         assert back["block_indices"] == block_indices and back["seed"] == seed and back["image_shape"] == list(image_shape)
