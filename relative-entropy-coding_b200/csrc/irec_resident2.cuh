@@ -124,6 +124,52 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
     }
 }
 
+// Canonical pairwise tree over the P chunk sums of a sample group (same totals, bit for bit, as the xor butterfly of
+// group_tree_sum: level `lev` adds the sums of lanes l and l ^ 2^lev, and a + b == b + a), done by recursive halving:
+// instead of both partners computing every total, the lane with bit `lev` clear keeps the even slots and its partner
+// the odd ones -- N/2 shuffles per level instead of N.  After log2(P) levels every lane owns ~N/P totals and stores
+// them itself.  N0 = NS * BMAX accumulators, slot a = k * BMAX + b  (sample k of the round, beam b).
+__host__ __device__ constexpr int r2_level_size(int n0, int lev) { return lev == 0 ? n0 : (r2_level_size(n0, lev - 1) + 1) / 2; }
+
+template <int N0, int N, int BMAX, int LEVEL>
+__device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, int s_first, int s_step, int S, int Bcur,
+                                              float* s_scores)
+{
+    constexpr int stride = 1 << LEVEL;
+    if constexpr (LEVEL < 5) {
+        if (stride < P) {
+            constexpr int M = (N + 1) / 2;
+            float o[M];
+            const bool hi = (lane & stride) != 0;
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                const float send = hi ? v[2 * i] : v[2 * i + 1];
+                const float keep = hi ? v[2 * i + 1] : v[2 * i];
+                o[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, stride));
+            }
+            if constexpr (N & 1) o[M - 1] = __fadd_rn(v[N - 1], __shfl_xor_sync(0xffffffffu, v[N - 1], stride));
+            r2_tree_store<N0, M, BMAX, LEVEL + 1>(o, P, lane, s_first, s_step, S, Bcur, s_scores);
+            return;
+        }
+    }
+    // LEVEL levels done: slot i of this lane is the total of the original slot found by unwinding the halvings
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int a = i;
+#pragma unroll
+        for (int lev = LEVEL - 1; lev >= 0; --lev) {
+            const int n_prev = r2_level_size(N0, lev);
+            a = ((n_prev & 1) && a == n_prev / 2) ? n_prev - 1 : 2 * a + ((lane >> lev) & 1);   // odd tail slot: replicated
+        }
+        const int k = a / BMAX, b = a - k * BMAX;
+        const int sk = s_first + k * s_step;
+        if (b < Bcur && sk < S) {
+            const float x = v[i];
+            s_scores[sk * Bcur + b] = (x == x) ? x : __int_as_float(0xff800000);
+        }
+    }
+}
+
 // one round of a warp: NS sample groups (group = the 32/P samples of one warp row), scores -> s_scores
 // tab_t: exponent table of this block size and partition ([S][row_stride] uint2) or nullptr
 template <int BMAX, int NS, bool TAB>
@@ -148,27 +194,12 @@ __device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* 
         for (int b = 0; b < BMAX; ++b) acc[k][b] = 0.f;
     }
     r2_score_chunk<BMAX, NS, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, tab_t, row, acc);
-    // canonical pairwise tree over the P chunk sums (xor butterfly, same order as group_tree_sum)
-    for (int stride = 1; stride < g.P; stride <<= 1) {
+    float v[NS * BMAX];
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
+    for (int k = 0; k < NS; ++k)
 #pragma unroll
-            for (int b = 0; b < BMAX; ++b)
-                acc[k][b] = __fadd_rn(acc[k][b], __shfl_xor_sync(0xffffffffu, acc[k][b], stride));
-    }
-    if (lg == 0) {
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            if (s[k] < S) {
-#pragma unroll
-                for (int b = 0; b < BMAX; ++b)
-                    if (b < Bcur) {
-                        const float v = acc[k][b];
-                        s_scores[s[k] * Bcur + b] = (v == v) ? v : __int_as_float(0xff800000);
-                    }
-            }
-        }
-    }
+        for (int b = 0; b < BMAX; ++b) v[k * BMAX + b] = acc[k][b];
+    r2_tree_store<NS * BMAX, NS * BMAX, BMAX, 0>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, S, Bcur, s_scores);
 }
 
 // all candidates of one partition: S samples x Bcur beams
