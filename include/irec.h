@@ -86,6 +86,11 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
                      int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status,
                      float* out_sample, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Which kernel irec_beam_encode runs for these sizes on the current device (diagnostics, tests, bench reports):
+ * 0 = one partition per launch (general path), 1 = k_beam_encode_resident, 2 = k_beam_encode_resident2 (persistent CTA per
+ * coder-block), 100 + G = k_beam_encode_cluster with G CTAs per coder-block (few blocks per launch: one image). */
+int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B);
+
 /* BeamSearchCoder.decode_block over nb blocks (beam_search_coder.py:124-148).  indices
  * [nb x max_aux] in partition order (the order encode returns), n_aux [nb]. */
 int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,

@@ -15,58 +15,6 @@
 #include <string.h>
 
 // =============================================================================================
-// per-dim schedule of partition t (beam_search_coder.py:64-77,108-109; coder.py:141-154)
-// float32 ops exactly in the reference's order; coefficients of the centred quadratic in float64.
-// =============================================================================================
-struct SchedOut {
-    float sa, A, E, M, cum_next;
-};
-__device__ __forceinline__ SchedOut beam_sched_dim(float cv, float tv, float dmu, float cum, float ratio)
-{
-    SchedOut o;
-    const float v = __fmul_rn(ratio, __fadd_rn(cv, -cum));
-    const float tot = __fadd_rn(v, cum);
-    const float m = __fdiv_rn(__fmul_rn(dmu, tot), cv);
-    const float s2 = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(tot, tot)), __fmul_rn(cv, cv)),
-                               __fdiv_rn(__fmul_rn(tot, __fadd_rn(cv, -tot)), cv));
-    o.sa = __fsqrt_rn(v);
-    o.A = (float)__dmul_rn(0.5, __dsub_rn(__ddiv_rn(1.0, (double)tot), __ddiv_rn(1.0, (double)s2)));
-    o.E = (float)__ddiv_rn((double)m, (double)tot);
-    o.M = m;
-    o.cum_next = __fadd_rn(cum, v);
-    return o;
-}
-
-// per-dim KL term in float64 (TFP kl_normal_normal)
-__device__ __forceinline__ double kl_dim(float tl, float ts, float pl, float ps)
-{
-    const double sp = (double)ps;
-    const double dl = __dsub_rn(log((double)ts), log(sp));
-    const double dm = __dsub_rn(__ddiv_rn((double)tl, sp), __ddiv_rn((double)pl, sp));
-    return __dsub_rn(__dadd_rn(__dmul_rn(0.5, __dmul_rn(dm, dm)), __dmul_rn(0.5, expm1(__dmul_rn(2.0, dl)))), dl);
-}
-
-__device__ __forceinline__ int n_aux_from_kl(float kl, float omega)
-{
-    const float q = __fdiv_rn(kl, omega);
-    if (!(q == q) || isinf(q)) return -1;
-    return (int)ceilf(q);
-}
-
-// canonical tree over nch chunk sums in shared memory (all threads call)
-__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch)
-{
-    const int P = next_pow2_int(nch);
-    __syncthreads();
-    for (int stride = 1; stride < P; stride <<= 1) {
-        for (int i = threadIdx.x * 2 * stride; i + stride < nch; i += blockDim.x * 2 * stride)
-            cs[i] = __dadd_rn(cs[i], cs[i + stride]);
-        __syncthreads();
-    }
-    return cs[0];
-}
-
-// =============================================================================================
 // k_kl_naux
 // =============================================================================================
 #define KL_MAX_CHUNKS 4096
@@ -1122,8 +1070,23 @@ size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, in
                             r2_table_bytes((int)max_block_dim, S, max_aux);
     const size_t general = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256 + sizeof(irec_record_t) * 32 + 256 +
                            irec_beam_step_workspace_bytes((int)max_block_dim, B);
-    (void)S;
-    return std::max(resident, general);
+    const size_t cluster = 512 + irec_cluster_hist_bytes(nb, max_aux) + r2_ws_order_bytes(nb) + r2_table_bytes((int)max_block_dim, S, max_aux);
+    return std::max(std::max(resident, general), cluster);
+}
+
+int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B)
+{
+    IREC_ENSURE_INIT();
+    if (nb <= 0 || S <= 0 || B <= 0 || B > 32 || max_block_dim <= 0) return 0;
+    const int rchoice = resident_choice();
+    if (irec_force_general()) return 0;
+    if (rchoice == 0) {
+        const int G = irec_cluster_choice(nb, (int)max_block_dim, S, B);
+        if (G > 0) return 100 + G;
+    }
+    if (rchoice != 1 && plan_resident2(nb, (int)max_block_dim, S, B).ok) return 2;
+    if (rchoice != 2 && plan_resident(nb, (int)max_block_dim, S, B).ok) return 1;
+    return 0;
 }
 
 int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
@@ -1143,6 +1106,30 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
     if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "beam_encode: kl_per_partition must be > 0");
 
     const int rchoice = resident_choice();
+    const int cluster_G = (irec_force_general() || rchoice != 0) ? 0 : irec_cluster_choice(nb, (int)max_block_dim, S, B);
+    if (cluster_G > 0) {
+        // few coder-blocks: one thread-block cluster per block (irec_cluster.cu)
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+        R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
+        int2* hist = reinterpret_cast<int2*>(w + 512);
+        int32_t* order = reinterpret_cast<int32_t*>(w + 512 + irec_cluster_hist_bytes(nb, max_aux));
+        if (cudaMemsetAsync(dplan, 0, sizeof(R2Plan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+        k_r2_plan<<<1, 1024, 0, s>>>(block_offsets, nb, dplan, order);
+        irec_count_launch();
+        const size_t tab_bytes = r2_table_bytes((int)max_block_dim, S, max_aux);
+        const uint2* tab = nullptr;
+        if (tab_bytes && !r2_no_table()) {
+            uint2* t = reinterpret_cast<uint2*>(w + 512 + irec_cluster_hist_bytes(nb, max_aux) + r2_ws_order_bytes(nb));
+            const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;
+            const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
+            k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, make_geom((int)max_block_dim).DP >> 2, t);
+            irec_count_launch();
+            tab = t;
+        }
+        return irec_launch_cluster(cluster_G, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim, omega,
+                                   S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
+                                   tab ? dplan : nullptr, tab, s);
+    }
     if (!irec_force_general() && rchoice != 1) {
         const ResidentPlan plan2 = plan_resident2(nb, (int)max_block_dim, S, B);
         if (plan2.ok) {

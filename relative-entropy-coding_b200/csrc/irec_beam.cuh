@@ -181,6 +181,58 @@ __device__ __forceinline__ void score_sample(const float* __restrict__ T, const 
     }
 }
 
+// =============================================================================================
+// per-dim schedule of partition t (beam_search_coder.py:64-77,108-109; coder.py:141-154)
+// float32 ops exactly in the reference's order; coefficients of the centred quadratic in float64.
+// =============================================================================================
+struct SchedOut {
+    float sa, A, E, M, cum_next;
+};
+__device__ __forceinline__ SchedOut beam_sched_dim(float cv, float tv, float dmu, float cum, float ratio)
+{
+    SchedOut o;
+    const float v = __fmul_rn(ratio, __fadd_rn(cv, -cum));
+    const float tot = __fadd_rn(v, cum);
+    const float m = __fdiv_rn(__fmul_rn(dmu, tot), cv);
+    const float s2 = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(tot, tot)), __fmul_rn(cv, cv)),
+                               __fdiv_rn(__fmul_rn(tot, __fadd_rn(cv, -tot)), cv));
+    o.sa = __fsqrt_rn(v);
+    o.A = (float)__dmul_rn(0.5, __dsub_rn(__ddiv_rn(1.0, (double)tot), __ddiv_rn(1.0, (double)s2)));
+    o.E = (float)__ddiv_rn((double)m, (double)tot);
+    o.M = m;
+    o.cum_next = __fadd_rn(cum, v);
+    return o;
+}
+
+// per-dim KL term in float64 (TFP kl_normal_normal)
+__device__ __forceinline__ double kl_dim(float tl, float ts, float pl, float ps)
+{
+    const double sp = (double)ps;
+    const double dl = __dsub_rn(log((double)ts), log(sp));
+    const double dm = __dsub_rn(__ddiv_rn((double)tl, sp), __ddiv_rn((double)pl, sp));
+    return __dsub_rn(__dadd_rn(__dmul_rn(0.5, __dmul_rn(dm, dm)), __dmul_rn(0.5, expm1(__dmul_rn(2.0, dl)))), dl);
+}
+
+__device__ __forceinline__ int n_aux_from_kl(float kl, float omega)
+{
+    const float q = __fdiv_rn(kl, omega);
+    if (!(q == q) || isinf(q)) return -1;
+    return (int)ceilf(q);
+}
+
+// canonical tree over nch chunk sums in shared memory (all threads call)
+__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch)
+{
+    const int P = next_pow2_int(nch);
+    __syncthreads();
+    for (int stride = 1; stride < P; stride <<= 1) {
+        for (int i = threadIdx.x * 2 * stride; i + stride < nch; i += blockDim.x * 2 * stride)
+            cs[i] = __dadd_rn(cs[i], cs[i + stride]);
+        __syncthreads();
+    }
+    return cs[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // block_topk: out[0..Kout) = the Kout = min(K, n) best of n candidates, best first, by
 // (score desc, id asc).  sc/id may live in shared or global memory; id == nullptr means id = i.

@@ -29,6 +29,14 @@ int irec_check_launch(const char* what);           // cudaGetLastError -> IREC_E
 void irec_count_launch();
 bool irec_force_general();                          // env IREC_FORCE_GENERAL=1 (tests)
 
+// irec_cluster.cu: one thread-block cluster per coder-block (few blocks per launch)
+int irec_cluster_choice(int nb, int max_D, int S, int B);       // cluster size to use, 0 = use the persistent kernels
+size_t irec_cluster_hist_bytes(int nb, int max_aux);
+int irec_launch_cluster(int G, const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                        const int64_t* gidx, const int64_t* offs, int nb, int max_D, float omega, int S, int B, int64_t seed,
+                        int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
+                        int2* hist, const int32_t* order, const void* plan, const void* tab, cudaStream_t s);
+
 #define IREC_ENSURE_INIT()                     \
     do {                                       \
         const int rc_init_ = irec_init();      \

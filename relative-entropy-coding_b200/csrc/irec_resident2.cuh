@@ -131,9 +131,18 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
 // them itself.  N0 = NS * BMAX accumulators, slot a = k * BMAX + b  (sample k of the round, beam b).
 __host__ __device__ constexpr int r2_level_size(int n0, int lev) { return lev == 0 ? n0 : (r2_level_size(n0, lev - 1) + 1) / 2; }
 
-template <int N0, int N, int BMAX, int LEVEL>
-__device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, int s_first, int s_step, int S, int Bcur,
-                                              float* s_scores)
+// Where a finished total goes.  sk = candidate sample, b = beam slot, dup = another lane holds the same total (the
+// replicated odd tail of a halving level; only sinks with expensive stores need to look at it).
+struct R2LocalSink {
+    float* s_scores; int S, Bcur;
+    __device__ __forceinline__ void operator()(int sk, int b, float x, bool) const
+    {
+        if (b < Bcur && sk < S) s_scores[sk * Bcur + b] = (x == x) ? x : __int_as_float(0xff800000);
+    }
+};
+
+template <int N0, int N, int BMAX, int LEVEL, class Sink>
+__device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, int s_first, int s_step, const Sink& sink)
 {
     constexpr int stride = 1 << LEVEL;
     if constexpr (LEVEL < 5) {
@@ -148,7 +157,7 @@ __device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, in
                 o[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, stride));
             }
             if constexpr (N & 1) o[M - 1] = __fadd_rn(v[N - 1], __shfl_xor_sync(0xffffffffu, v[N - 1], stride));
-            r2_tree_store<N0, M, BMAX, LEVEL + 1>(o, P, lane, s_first, s_step, S, Bcur, s_scores);
+            r2_tree_store<N0, M, BMAX, LEVEL + 1, Sink>(o, P, lane, s_first, s_step, sink);
             return;
         }
     }
@@ -156,17 +165,16 @@ __device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, in
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         int a = i;
+        bool dup = false;
 #pragma unroll
         for (int lev = LEVEL - 1; lev >= 0; --lev) {
             const int n_prev = r2_level_size(N0, lev);
-            a = ((n_prev & 1) && a == n_prev / 2) ? n_prev - 1 : 2 * a + ((lane >> lev) & 1);   // odd tail slot: replicated
+            const bool tail = (n_prev & 1) && a == n_prev / 2;                 // odd tail slot: replicated in both partners
+            dup = dup || (tail && ((lane >> lev) & 1));
+            a = tail ? n_prev - 1 : 2 * a + ((lane >> lev) & 1);
         }
         const int k = a / BMAX, b = a - k * BMAX;
-        const int sk = s_first + k * s_step;
-        if (b < Bcur && sk < S) {
-            const float x = v[i];
-            s_scores[sk * Bcur + b] = (x == x) ? x : __int_as_float(0xff800000);
-        }
+        sink(s_first + k * s_step, b, v[i], dup);
     }
 }
 
@@ -199,7 +207,8 @@ __device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* 
     for (int k = 0; k < NS; ++k)
 #pragma unroll
         for (int b = 0; b < BMAX; ++b) v[k * BMAX + b] = acc[k][b];
-    r2_tree_store<NS * BMAX, NS * BMAX, BMAX, 0>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, S, Bcur, s_scores);
+    const R2LocalSink sink{ s_scores, S, Bcur };
+    r2_tree_store<NS * BMAX, NS * BMAX, BMAX, 0, R2LocalSink>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, sink);
 }
 
 // all candidates of one partition: S samples x Bcur beams
@@ -243,6 +252,7 @@ struct R2Plan {
     int32_t pad;
 };
 
+#ifndef IREC_R2_DEVICE_ONLY      // the __global__ kernels below belong to irec_beam.cu only
 // Also writes `order`: the coder-blocks sorted by decreasing size (counting sort), the sequence in which the
 // persistent CTAs draw them from the queue -- the short blocks of a tensor (its last, partial block) go last and
 // fill the tail of the launch instead of leaving SMs idle behind a full-size block.
@@ -368,6 +378,8 @@ __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan
     }
 }
 
+#endif  // IREC_R2_DEVICE_ONLY
+
 // Winners' new beams, in place (beam_search_coder.py:92-93): beam_j <- beam_{b_j} + a(s_j, b_j).
 // One WARP per winner j (s_list[j] = s_j, s_list[32 + j] = b_j), lanes stride over the quad columns: the winner's
 // exponent row is one coalesced 8-byte load per lane and quad, all issued up front; the parent quad is a conflict-free
@@ -442,6 +454,7 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
     }
 }
 
+#ifndef IREC_R2_DEVICE_ONLY
 struct Resident2Args {
     const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
     const int64_t* gidx; const int64_t* offs; int nb;
@@ -634,3 +647,4 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         }
     }
 }
+#endif  // IREC_R2_DEVICE_ONLY

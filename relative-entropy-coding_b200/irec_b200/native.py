@@ -39,6 +39,7 @@ _SIGNATURES = {
     "irec_beam_encode_workspace_bytes": (C.c_size_t, [_i32, _i64, _i32, _i32, _i32]),
     "irec_beam_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i32, _i32, _i64,
                                    _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "irec_beam_encode_path": (C.c_int, [_i32, _i64, _i32, _i32]),
     "irec_beam_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
     "irec_beam_state_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "irec_beam_state_init": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i64, _vp]),

@@ -106,26 +106,63 @@ def run_beam_case(cuda, recipe, D, data_seed, omega, extra, B, seed):
     assert np.array_equal(bits(dec.cpu().numpy().reshape(-1)), bits(odec))
 
 
-@pytest.mark.parametrize("kernel", ["resident2", "resident2-notable", "resident1"])
+KERNEL_ENV = {
+    "resident1": {"IREC_RESIDENT": "1"},                              # k_beam_encode_resident
+    "resident2": {"IREC_RESIDENT": "2"},                              # k_beam_encode_resident2 (discrete-log table addressing)
+    "resident2-notable": {"IREC_RESIDENT": "2", "IREC_R2_NO_TABLE": "1"},   # exponents from Philox + dlog in place
+    "cluster8": {"IREC_CLUSTER": "8"},                                # k_beam_encode_cluster, 8 CTAs per coder-block
+    "cluster4": {"IREC_CLUSTER": "4"},
+    "cluster8-notable": {"IREC_CLUSTER": "8", "IREC_R2_NO_TABLE": "1"},
+}
+
+
+class kernel_env:
+    def __init__(self, kernel):
+        self.env = KERNEL_ENV[kernel]
+
+    def __enter__(self):
+        for k in ("IREC_FORCE_GENERAL", "IREC_RESIDENT", "IREC_R2_NO_TABLE", "IREC_CLUSTER"):
+            os.environ.pop(k, None)
+        os.environ.update(self.env)
+
+    def __exit__(self, *exc):
+        for k in self.env:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("kernel", list(KERNEL_ENV))
 @pytest.mark.parametrize("case", BEAM_CASES, ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in BEAM_CASES])
 def test_beam_resident_vs_oracle(cuda, case, kernel):
-    """both generations of the persistent per-block kernel (IREC_RESIDENT=1: k_beam_encode_resident,
-    default: k_beam_encode_resident2 with discrete-log table addressing) are bit-identical to the oracle"""
-    os.environ.pop("IREC_FORCE_GENERAL", None)
-    if kernel == "resident1":
-        os.environ["IREC_RESIDENT"] = "1"
-    if kernel == "resident2-notable":
-        os.environ["IREC_R2_NO_TABLE"] = "1"      # exponents from Philox + dlog in place instead of the per-launch table
-    try:
+    """both generations of the persistent per-block kernel and the cluster-per-block kernel (with and without the
+    per-launch exponent table) are bit-identical to the oracle"""
+    with kernel_env(kernel):
         run_beam_case(cuda, *case)
-    finally:
-        os.environ.pop("IREC_RESIDENT", None)
-        os.environ.pop("IREC_R2_NO_TABLE", None)
 
 
-def test_beam_ragged_blocks_one_launch(cuda):
+@pytest.mark.parametrize("kernel", ["resident2", "cluster8", "cluster4"])
+def test_beam_ragged_blocks_one_launch(cuda, kernel):
     """four different block sizes in ONE launch: two get a per-launch exponent table, the others generate their
     candidate exponents in place; every block must equal the oracle on its own slice"""
+    with kernel_env(kernel):
+        _ragged_blocks(cuda)
+
+
+def test_default_kernel_choice(cuda):
+    """few coder-blocks per launch (one image: 9 / 13 blocks) -> the cluster kernel; a batch -> the persistent kernel"""
+    from irec_b200 import native as N
+    lib = N.lib()
+    for k in ("IREC_FORCE_GENERAL", "IREC_RESIDENT", "IREC_CLUSTER"):
+        os.environ.pop(k, None)
+    assert lib.irec_beam_encode_path(9, 1000, 36, 20) == 108        # 100 + cluster size
+    assert lib.irec_beam_encode_path(13, 1000, 20, 10) == 108
+    assert lib.irec_beam_encode_path(24, 1000, 36, 20) == 104
+    assert lib.irec_beam_encode_path(302, 1000, 20, 10) == 2
+    assert lib.irec_beam_encode_path(1152, 1000, 36, 20) == 2
+    assert lib.irec_beam_encode_path(1, 64, 36, 1) == 2
+    assert lib.irec_beam_encode_path(1, 2500, 36, 4) == 0
+
+
+def _ragged_blocks(cuda):
     import torch
     from irec_b200 import engine
     sizes = [100, 200, 37, 1000, 200, 100, 5]
