@@ -50,6 +50,9 @@ def main():
     byfile = collections.Counter()
     for k, v in agg.items():
         byfile[k[0] if k else None] += v
+    if os.environ.get("IREC_HOTSPOT_DUMP"):
+        import pickle
+        pickle.dump((dict(agg), tot), open(os.environ["IREC_HOTSPOT_DUMP"], "wb"))
     print("| file:line | % of warp samples |\n|---|---|")
     for k, v in agg.most_common(40):
         print(f"| {k[0]}:{k[1]} | {100 * v / tot:.2f} |" if k else f"| ? | {100 * v / tot:.2f} |")
