@@ -129,16 +129,46 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
 // instead of both partners computing every total, the lane with bit `lev` clear keeps the even slots and its partner
 // the odd ones -- N/2 shuffles per level instead of N.  After log2(P) levels every lane owns ~N/P totals and stores
 // them itself.  N0 = NS * BMAX accumulators, slot a = k * BMAX + b  (sample k of the round, beam b).
-__host__ __device__ constexpr int r2_level_size(int n0, int lev) { return lev == 0 ? n0 : (r2_level_size(n0, lev - 1) + 1) / 2; }
+template <int N0, int LEV>
+struct R2LevelSize { static constexpr int value = (R2LevelSize<N0, LEV - 1>::value + 1) / 2; };   // slots per lane after LEV halvings
+template <int N0>
+struct R2LevelSize<N0, 0> { static constexpr int value = N0; };
+
+// slot a of a lane after LEV halving levels -> original slot (and whether another lane holds the same total)
+template <int N0, int LEV>
+__device__ __forceinline__ int r2_unwind(int a, int lane, bool& dup)
+{
+    if constexpr (LEV == 0) {
+        return a;
+    } else {
+        constexpr int n_prev = R2LevelSize<N0, LEV - 1>::value;
+        const int bit = (lane >> (LEV - 1)) & 1;
+        const bool tail = (n_prev & 1) && a == n_prev / 2;                    // odd tail slot: replicated in both partners
+        dup = dup || (tail && bit);
+        return r2_unwind<N0, LEV - 1>(tail ? n_prev - 1 : 2 * a + bit, lane, dup);
+    }
+}
 
 // Where a finished total goes.  sk = candidate sample, b = beam slot, dup = another lane holds the same total (the
 // replicated odd tail of a halving level; only sinks with expensive stores need to look at it).
 struct R2LocalSink {
-    float* s_scores; int S, Bcur;
+    float* s_scores; int S, Bcur, boff;      // boff: first beam slot of the pass (beams are scored in passes of R2Pass::HB)
     __device__ __forceinline__ void operator()(int sk, int b, float x, bool) const
     {
+        b += boff;
         if (b < Bcur && sk < S) s_scores[sk * Bcur + b] = (x == x) ? x : __int_as_float(0xff800000);
     }
+};
+
+// Beam slots per scoring pass.  One pass keeps NS * HB accumulators in registers; with all BMAX = 20 slots in one pass
+// (60 accumulators + the gather operands) ptxas sits at the 168-register cap of a 384-thread CTA and, depending on
+// unrelated code, serialises the quantile gathers (load -> immediate use).  Two passes of 10 re-read the per-dim
+// coefficients and the exponents once more (+2.5 % shared-memory wavefronts) and leave ~40 registers for loads in flight.
+template <int BMAX>
+struct R2Pass {
+    static constexpr int N = (BMAX > 10) ? 2 : 1;
+    static constexpr int HB = BMAX / N;
+    static_assert(HB * N == BMAX, "BMAX must split evenly");
 };
 
 template <int N0, int N, int BMAX, int LEVEL, class Sink>
@@ -164,15 +194,8 @@ __device__ __forceinline__ void r2_tree_store(float (&v)[N], int P, int lane, in
     // LEVEL levels done: slot i of this lane is the total of the original slot found by unwinding the halvings
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        int a = i;
         bool dup = false;
-#pragma unroll
-        for (int lev = LEVEL - 1; lev >= 0; --lev) {
-            const int n_prev = r2_level_size(N0, lev);
-            const bool tail = (n_prev & 1) && a == n_prev / 2;                 // odd tail slot: replicated in both partners
-            dup = dup || (tail && ((lane >> lev) & 1));
-            a = tail ? n_prev - 1 : 2 * a + ((lane >> lev) & 1);
-        }
+        const int a = r2_unwind<N0, LEVEL>(i, lane, dup);
         const int k = a / BMAX, b = a - k * BMAX;
         sink(s_first + k * s_step, b, v[i], dup);
     }
@@ -188,27 +211,34 @@ __device__ __forceinline__ void r2_score_round(const char* T2b, const uint16_t* 
                                                int sg_first, int sg_stride, int S, int Bcur, float* s_scores)
 {
     const int lg = lane & (g.P - 1);
-    int s[NS];
+    constexpr int HB = R2Pass<BMAX>::HB;
     uint64_t jb[NS];
     uint32_t row[NS];                       // uint2 index of (sample row, first quad of the chunk) in tab_t
-    float acc[NS][BMAX];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        s[k] = (sg_first + k * sg_stride) * g.SPW + lane / g.P;
-        const int sc = min(s[k], S - 1);
+        const int sk = (sg_first + k * sg_stride) * g.SPW + lane / g.P;
+        const int sc = min(sk, S - 1);
         jb[k] = TAB ? 0ull : (uint64_t)sc * (uint64_t)g.D + (uint64_t)(32 * lg);
         row[k] = (uint32_t)(sc * row_stride + lg);
-#pragma unroll
-        for (int b = 0; b < BMAX; ++b) acc[k][b] = 0.f;
     }
-    r2_score_chunk<BMAX, NS, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, tab_t, row, acc);
-    float v[NS * BMAX];
+#pragma unroll 1
+    for (int boff = 0; boff < BMAX; boff += HB) {
+        if (boff >= Bcur) break;            // unused slots (warp-uniform)
+        float acc[NS][HB];
 #pragma unroll
-    for (int k = 0; k < NS; ++k)
+        for (int k = 0; k < NS; ++k)
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) v[k * BMAX + b] = acc[k][b];
-    const R2LocalSink sink{ s_scores, S, Bcur };
-    r2_tree_store<NS * BMAX, NS * BMAX, BMAX, 0, R2LocalSink>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, sink);
+            for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
+        r2_score_chunk<HB, NS, TAB>(T2b, dl4, cb4 + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2), g.DP >> 2, g.P, lg, st, jb,
+                                    tab_t, row, acc);
+        float v[NS * HB];
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
+        const R2LocalSink sink{ s_scores, S, Bcur, boff };
+        r2_tree_store<NS * HB, NS * HB, HB, 0, R2LocalSink>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, sink);
+    }
 }
 
 // all candidates of one partition: S samples x Bcur beams
@@ -380,26 +410,43 @@ __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan
 
 #endif  // IREC_R2_DEVICE_ONLY
 
-// Winners' new beams, in place (beam_search_coder.py:92-93): beam_j <- beam_{b_j} + a(s_j, b_j).
+// Winners' new beams, in place (beam_search_coder.py:92-93): beam_j <- beam_{b_j} + a(s_j, b_j), fused with the
+// schedule of the NEXT auxiliary variable (beam_search_coder.py:64-77), which does not depend on the winners.
 // One WARP per winner j (s_list[j] = s_j, s_list[32 + j] = b_j), lanes stride over the quad columns: the winner's
 // exponent row is one coalesced 8-byte load per lane and quad, all issued up front; the parent quad is a conflict-free
 // LDS.128.  Every new value is held in registers until a CTA barrier, then stored -- a parent may be another winner's
-// destination.  Kept out of line so that it does not disturb the register allocation of the scoring loop.
-template <int BMAX>
+// destination.  The next schedule (float64 divisions, global scratch loads) is computed into registers between the
+// winners' loads and the barrier, so its latency overlaps the table round trips, and is stored after the barrier
+// (the winners still read this variable's sigma_aux before it).  hs_new: hash sums of the new beams -> the next
+// table offsets c_b.  Kept out of line so that it does not disturb the register allocation of the scoring loop.
+struct R2NextSched {
+    int on;                        // 0: last auxiliary variable, nothing to prepare
+    float ratio;                   // power-law ratio of the next auxiliary variable
+    const float* g_cv; const float* g_tv; const float* g_dmu; float* g_cum;     // per-CTA global scratch
+    int off_A, off_E, off_M;       // byte offsets of the shared arrays
+    int off_hs_new;                // int32[32] hash sums of the new beams
+};
+
+template <int BMAX, int WPW, bool TAB>
 __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __restrict__ dl4, int off_cb, int off_list,
                                               int off_sa, int off_beams, int DP, int P,
-                                              int D, int Kout, const TfStream st, const uint2* __restrict__ tab_t, int row_stride)
+                                              int D, int Kout, const TfStream st, const uint2* __restrict__ tab_t, int row_stride,
+                                              const R2NextSched ns)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];      // byte offsets keep the accesses LDS/STS (not generic)
     const char* T2b = reinterpret_cast<const char*>(smem_raw + off_T2);
-    const uint32_t* s_cb = reinterpret_cast<const uint32_t*>(smem_raw + off_cb);
+    uint32_t* s_cb = reinterpret_cast<uint32_t*>(smem_raw + off_cb);
     const int32_t* s_list = reinterpret_cast<const int32_t*>(smem_raw + off_list);
     const float4* sa4 = reinterpret_cast<const float4*>(smem_raw + off_sa);
     float4* beams4 = reinterpret_cast<float4*>(smem_raw + off_beams);
-    constexpr int WPW = (BMAX + 7) / 8;                             // winners per warp (the CTA has at least 8 warps)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int nq = DP >> 2, lgP = __ffs(P) - 1;                     // P is a power of two; nq <= 256
     float4 nv[WPW][8];
+#pragma unroll
+    for (int w = 0; w < WPW; ++w)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nv[w][i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int w = 0; w < WPW; ++w) {
         const int j = warp + w * nwarps;
@@ -407,7 +454,7 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
             const int sj = s_list[j], bj = s_list[32 + j];
             const uint32_t cb = s_cb[bj];
             uint2 ex[8];
-            if (tab_t) {
+            if (TAB) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int qq = lane + 32 * i;
@@ -422,7 +469,7 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (qq < nq && d0 < D) {
                     uint32_t e0, e1, e2, e3;
-                    if (tab_t) {
+                    if (TAB) {
                         r2_unpack(ex[i], e0, e1, e2, e3);
                     } else {
                         const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
@@ -440,6 +487,27 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
             }
         }
     }
+    // ---- next schedule into registers: thread owns dims tid, tid + nt, ... (at most 4: DP <= 1024, nt >= 256) ----
+    SchedOut so[4];
+    uint32_t cb_next = 0u, live = 0u;
+    if (ns.on) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = tid + r * nt;
+            so[r].sa = 0.f; so[r].A = 0.f; so[r].E = 0.f; so[r].M = 0.f; so[r].cum_next = 0.f;
+            if (i < DP) {
+                const float cv = ns.g_cv[i];
+                if (cv != 0.f) {                     // padding stays zero: nothing to store
+                    so[r] = beam_sched_dim(cv, ns.g_tv[i], ns.g_dmu[i], ns.g_cum[i], ns.ratio);
+                    live |= 1u << r;
+                }
+            }
+        }
+        if (tid < 32) {
+            const int32_t* hs_new = reinterpret_cast<const int32_t*>(smem_raw + ns.off_hs_new);
+            cb_next = tid < Kout ? (uint32_t)__ldg(dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
+        }
+    }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < WPW; ++w) {
@@ -451,6 +519,20 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
                 if (qq < nq) beams4[j * nq + qq] = nv[w][i];      // pure padding columns receive zeros (they were zero)
             }
         }
+    }
+    if (ns.on) {
+        float* s_sa = reinterpret_cast<float*>(smem_raw + off_sa);
+        float* s_A = reinterpret_cast<float*>(smem_raw + ns.off_A);
+        float* s_E = reinterpret_cast<float*>(smem_raw + ns.off_E);
+        float* s_M = reinterpret_cast<float*>(smem_raw + ns.off_M);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = tid + r * nt;
+            if ((live >> r) & 1u) {
+                s_sa[i] = so[r].sa; s_A[i] = so[r].A; s_E[i] = so[r].E; s_M[i] = so[r].M; ns.g_cum[i] = so[r].cum_next;
+            }
+        }
+        if (tid < 32) s_cb[tid] = cb_next;
     }
 }
 
@@ -565,9 +647,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         const float4* M4 = reinterpret_cast<const float4*>(s_M);
         const float4* beams4 = reinterpret_cast<const float4*>(s_beams);
 
-        for (int t = 0; t < n_aux; ++t) {
-            // ---- schedule (beam_search_coder.py:64-77) + the beams' table offsets c_b = dlog(simple_hash) ----
-            const float ratio = a.ratio_tab[n_aux - 1 - t];
+        // ---- schedule of the first auxiliary variable (beam_search_coder.py:64-77); the later ones are prepared inside
+        //      r2_rematerialise while the winners of the previous variable are re-materialised ----
+        {
+            const float ratio = a.ratio_tab[n_aux - 1];
             for (int i = tid; i < g.DP; i += nt) {
                 const float cv = g_cv[i];
                 if (cv != 0.f) {                   // padding stays zero
@@ -575,9 +658,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
                     s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; g_cum[i] = o.cum_next;
                 }
             }
-            const int32_t* hs = s_hsum + 32 * hb;
-            if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs[tid]) - 1)) : 0u;
+            if (tid < 32) s_cb[tid] = tid < 1 ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(0) - 1)) : 0u;   // empty index row
             __syncthreads();
+        }
+
+        for (int t = 0; t < n_aux; ++t) {
+            const int32_t* hs = s_hsum + 32 * hb;
 
             // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102) ----
             const TfStream st = tf_stream_seeded(a.seed + t, a.seed + t);
@@ -598,32 +684,41 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
             // ---- top-B (beam_search_coder.py:86-89,104-106) ----
             const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl);
 
-            // ---- history + hash sums of the new beams (beam_search_coder.py:92-95) ----
+            // ---- history + hash sums of the new beams (beam_search_coder.py:92-95); (s_j, b_j) for the re-materialisation
+            //      (s_list is free after block_topk) ----
             int32_t* hs_new = s_hsum + 32 * (hb ^ 1);
             if (tid < Kout) {
                 const int f = s_wid[tid];
                 const int sj = f / Bcur, bj = f - sj * Bcur;
                 hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
                 hs_new[tid] = hsum_extend(hs[bj], sj, t);
-            }
-
-            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93) ----
-            // One thread owns one half quad column (2 dims) of the beam matrix: it reads the parents of all winners
-            // for its dims into registers, then overwrites the column -- in place, no barrier, no cross-thread hazard.
-            if (tid < Kout) {
-                const int f = s_wid[tid];
-                const int sj = f / Bcur;
-                s_list[tid] = sj; s_list[32 + tid] = f - sj * Bcur;       // (s_j, b_j); s_list is free after block_topk
+                s_list[tid] = sj; s_list[32 + tid] = bj;
             }
             __syncthreads();
+
+            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93), and prepare the next variable ----
             {
                 const unsigned char* b0 = smem_raw;
-                r2_rematerialise<BMAX>((int)(reinterpret_cast<const unsigned char*>(s_T2) - b0), a.dl4,
-                                       (int)(reinterpret_cast<const unsigned char*>(s_cb) - b0),
-                                       (int)(reinterpret_cast<const unsigned char*>(s_list) - b0),
-                                       (int)(reinterpret_cast<const unsigned char*>(s_sa) - b0),
-                                       (int)(reinterpret_cast<const unsigned char*>(s_beams) - b0),
-                                       g.DP, g.P, D, Kout, st, tab_t, row_stride);
+                R2NextSched ns;
+                ns.on = (t + 1 < n_aux) ? 1 : 0;
+                ns.ratio = ns.on ? a.ratio_tab[n_aux - 2 - t] : 0.f;
+                ns.g_cv = g_cv; ns.g_tv = g_tv; ns.g_dmu = g_dmu; ns.g_cum = g_cum;
+                ns.off_A = (int)(reinterpret_cast<const unsigned char*>(s_A) - b0);
+                ns.off_E = (int)(reinterpret_cast<const unsigned char*>(s_E) - b0);
+                ns.off_M = (int)(reinterpret_cast<const unsigned char*>(s_M) - b0);
+                ns.off_hs_new = (int)(reinterpret_cast<const unsigned char*>(hs_new) - b0);
+                const int o_T2 = (int)(reinterpret_cast<const unsigned char*>(s_T2) - b0);
+                const int o_cb = (int)(reinterpret_cast<const unsigned char*>(s_cb) - b0);
+                const int o_list = (int)(reinterpret_cast<const unsigned char*>(s_list) - b0);
+                const int o_sa = (int)(reinterpret_cast<const unsigned char*>(s_sa) - b0);
+                const int o_beams = (int)(reinterpret_cast<const unsigned char*>(s_beams) - b0);
+                constexpr int W12 = (BMAX + 11) / 12, W8 = (BMAX + 7) / 8;      // winners per warp with 12 / at least 8 warps
+                if (!tab_t)
+                    r2_rematerialise<BMAX, W8, false>(o_T2, a.dl4, o_cb, o_list, o_sa, o_beams, g.DP, g.P, D, Kout, st, tab_t, row_stride, ns);
+                else if (W12 < W8 && nt >= 384)
+                    r2_rematerialise<BMAX, W12, true>(o_T2, a.dl4, o_cb, o_list, o_sa, o_beams, g.DP, g.P, D, Kout, st, tab_t, row_stride, ns);
+                else
+                    r2_rematerialise<BMAX, W8, true>(o_T2, a.dl4, o_cb, o_list, o_sa, o_beams, g.DP, g.P, D, Kout, st, tab_t, row_stride, ns);
             }
             __syncthreads();
             Bcur = Kout;
