@@ -442,6 +442,49 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int nq = DP >> 2, lgP = __ffs(P) - 1;                     // P is a power of two; nq <= 256
+    // 1. every global load up front: the winners' exponent rows and the schedule inputs (L2 round trips overlap)
+    uint2 ex[WPW][8];
+    int sjw[WPW], bjw[WPW];
+#pragma unroll
+    for (int w = 0; w < WPW; ++w) {
+        const int j = warp + w * nwarps;
+        const bool on = j < Kout;
+        sjw[w] = on ? s_list[j] : 0;
+        bjw[w] = on ? s_list[32 + j] : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int qq = lane + 32 * i;
+            ex[w][i] = (TAB && on && qq < nq) ? __ldg(tab_t + (size_t)sjw[w] * row_stride + qq) : make_uint2(0u, 0u);
+        }
+    }
+    float g_in[4][4];
+    uint32_t cb_next = 0u, live = 0u;
+    if (ns.on) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = tid + r * nt;
+            const bool on = i < DP;
+            g_in[r][0] = on ? ns.g_cv[i] : 0.f;
+            g_in[r][1] = on ? ns.g_tv[i] : 0.f;
+            g_in[r][2] = on ? ns.g_dmu[i] : 0.f;
+            g_in[r][3] = on ? ns.g_cum[i] : 0.f;
+        }
+        if (tid < 32) {
+            const int32_t* hs_new = reinterpret_cast<const int32_t*>(smem_raw + ns.off_hs_new);
+            cb_next = tid < Kout ? (uint32_t)__ldg(dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
+        }
+    }
+    // 2. next schedule into registers: thread owns dims tid, tid + nt, ... (at most 4: DP <= 1024, nt >= 256)
+    SchedOut so[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        so[r].sa = 0.f; so[r].A = 0.f; so[r].E = 0.f; so[r].M = 0.f; so[r].cum_next = 0.f;
+        if (ns.on && g_in[r][0] != 0.f) {            // padding (cv == 0) stays zero: nothing to store
+            so[r] = beam_sched_dim(g_in[r][0], g_in[r][1], g_in[r][2], g_in[r][3], ns.ratio);
+            live |= 1u << r;
+        }
+    }
+    // 3. the winners' new values
     float4 nv[WPW][8];
 #pragma unroll
     for (int w = 0; w < WPW; ++w)
@@ -451,16 +494,8 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
     for (int w = 0; w < WPW; ++w) {
         const int j = warp + w * nwarps;
         if (j < Kout) {
-            const int sj = s_list[j], bj = s_list[32 + j];
+            const int sj = sjw[w], bj = bjw[w];
             const uint32_t cb = s_cb[bj];
-            uint2 ex[8];
-            if (TAB) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int qq = lane + 32 * i;
-                    ex[i] = qq < nq ? __ldg(tab_t + (size_t)sj * row_stride + qq) : make_uint2(0u, 0u);
-                }
-            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int qq = lane + 32 * i;
@@ -470,7 +505,7 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
                 if (qq < nq && d0 < D) {
                     uint32_t e0, e1, e2, e3;
                     if (TAB) {
-                        r2_unpack(ex[i], e0, e1, e2, e3);
+                        r2_unpack(ex[w][i], e0, e1, e2, e3);
                     } else {
                         const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
                         e0 = r2_exp4(dl4, u.x); e1 = r2_exp4(dl4, u.y); e2 = r2_exp4(dl4, u.z); e3 = r2_exp4(dl4, u.w);
@@ -485,27 +520,6 @@ __device__ __noinline__ void r2_rematerialise(int off_T2, const uint16_t* __rest
                 }
                 nv[w][i] = o;
             }
-        }
-    }
-    // ---- next schedule into registers: thread owns dims tid, tid + nt, ... (at most 4: DP <= 1024, nt >= 256) ----
-    SchedOut so[4];
-    uint32_t cb_next = 0u, live = 0u;
-    if (ns.on) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int i = tid + r * nt;
-            so[r].sa = 0.f; so[r].A = 0.f; so[r].E = 0.f; so[r].M = 0.f; so[r].cum_next = 0.f;
-            if (i < DP) {
-                const float cv = ns.g_cv[i];
-                if (cv != 0.f) {                     // padding stays zero: nothing to store
-                    so[r] = beam_sched_dim(cv, ns.g_tv[i], ns.g_dmu[i], ns.g_cum[i], ns.ratio);
-                    live |= 1u << r;
-                }
-            }
-        }
-        if (tid < 32) {
-            const int32_t* hs_new = reinterpret_cast<const int32_t*>(smem_raw + ns.off_hs_new);
-            cb_next = tid < Kout ? (uint32_t)__ldg(dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
         }
     }
     __syncthreads();

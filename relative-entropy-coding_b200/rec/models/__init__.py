@@ -1,5 +1,12 @@
-"""rec.models -- only the coder-facing glue of the reference's models: the NN layers are out of
-scope, the compress/decompress loops around `coder.encode` / `coder.decode` / the `.rec` container are here."""
-from .latent_hierarchy import LatentHierarchy, SyntheticLadder
+"""rec.models -- the coder-facing side of the reference's models.
 
-__all__ = ["LatentHierarchy", "SyntheticLadder"]
+  * latent_hierarchy : the compress / decompress loops over an abstract ladder of priors/posteriors (synthetic stand-in
+                       for the networks; what the benches use)
+  * resnet_vae       : the lossless bidirectional ResNet VAE (rec/models/resnet_vae.py) in plain PyTorch, random-init
+  * lossy            : the two-level lossy VAE (rec/models/lossy/large_2_level_vae.py) in plain PyTorch, random-init
+The networks are callers of the hot path, not part of it: cuDNN convolutions, no custom kernels, no training loop."""
+from .latent_hierarchy import LatentHierarchy, SyntheticLadder
+from .lossy import Large2LevelVAE
+from .resnet_vae import BidirectionalResNetVAE
+
+__all__ = ["LatentHierarchy", "SyntheticLadder", "BidirectionalResNetVAE", "Large2LevelVAE"]
