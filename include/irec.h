@@ -47,6 +47,14 @@ int irec_init(void);
 int irec_get_ndtri_table(float* host_out);
 /* HOST: ratio(i) as the library computes it */
 float irec_aux_ratio(int i);
+/* Learned auxiliary variance ratios (GaussianCoder(extrapolate_auxiliary_ratios=False),
+ * rec/coding/coder.py:197-231: `aux_variable_variance_ratios[index]` instead of the power law).
+ * Installs a DEVICE table of n float32 ratios for every later call made by the CALLING HOST THREAD
+ * (encode, decode, the sharded state functions) until it is cleared with (NULL, 0).  The table is
+ * borrowed: it must stay alive until the work enqueued under it has finished.  A coder-block that needs
+ * more auxiliary variables than n reports IREC_BLK_TOO_LONG (the reference raises CodingError there,
+ * coder.py:226-231). */
+int irec_set_thread_aux_ratios(const float* dev_ratios, int n);
 
 /* HOST helpers restating TensorFlow's seed plumbing (python/framework/random_seed.py,
  * python/eager/context.py): op seed of the first unseeded random op after tf.random.set_seed(seed),

@@ -298,8 +298,21 @@ void orc_ndtri_table(float* T)
 /* ------------------------------------------------------------------------------------------
  * coder.py:16,218-220  ratio(i) = float32(np.power(i + 1., -0.7864636765648174))
  * ---------------------------------------------------------------------------------------- */
+/* coder.py:197-231: learned ratios (extrapolate_auxiliary_ratios=False) replace the power law; per-thread override,
+ * set by orc_set_aux_ratios(host table, n) and cleared with (NULL, 0) */
+#define ORC_MAX_LEARNED 4096
+static __thread float g_learned[ORC_MAX_LEARNED];
+static __thread int g_n_learned = 0;
+int orc_set_aux_ratios(const float* ratios, int n)
+{
+    if (n < 0 || n > ORC_MAX_LEARNED || (n > 0 && !ratios)) return -1;
+    for (int i = 0; i < n; ++i) g_learned[i] = ratios[i];
+    g_n_learned = n;
+    return 0;
+}
 float orc_aux_ratio(int i)
 {
+    if (g_n_learned > 0) return (i >= 0 && i < g_n_learned) ? g_learned[i] : 0.0f;
     return (float)pow((double)i + 1.0, -0.7864636765648174);
 }
 

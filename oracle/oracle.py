@@ -99,6 +99,18 @@ def aux_ratio(i):
     return float(lib().orc_aux_ratio(int(i)))
 
 
+def set_aux_ratios(ratios=None):
+    """learned auxiliary ratios for the calls that follow on this thread (None restores the power law)"""
+    l = lib()
+    l.orc_set_aux_ratios.restype = C.c_int
+    l.orc_set_aux_ratios.argtypes = [C.c_void_p, C.c_int]
+    if ratios is None:
+        assert l.orc_set_aux_ratios(None, 0) == 0
+        return
+    r = _f32(ratios)
+    assert l.orc_set_aux_ratios(_p(r), int(r.size)) == 0
+
+
 def simple_hash(indices):
     a = np.ascontiguousarray(np.asarray(indices, np.int32))
     return int(lib().orc_simple_hash(_p(a, C.c_int32), C.c_int(a.size)))

@@ -925,7 +925,7 @@ int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* ga
     if (nb <= 0) return IREC_OK;
     k_beam_decode<<<std::min(nb, 8 * irec_device().sm_count), 256, 0, (cudaStream_t)stream>>>(
         p_loc, p_scale, gather_idx, block_offsets, nb, seed, indices, max_aux, n_aux, irec_device().d_T,
-        irec_device().d_ratio, out_sample);
+        irec_ratio_tab(), out_sample);
     irec_count_launch();
     return irec_check_launch("k_beam_decode");
 }
@@ -942,7 +942,7 @@ int irec_beam_state_init(void* state, const float* t_loc, const float* t_scale, 
     if (((D + 31) >> 5) > KL_MAX_CHUNKS) return irec_fail(IREC_E_CAPACITY, "beam_state_init: D too large (max 131072 per block)");
     if ((int64_t)S * B >= (1LL << 31)) return irec_fail(IREC_E_CAPACITY, "beam_state_init: S*B must be < 2^31");
     k_gp_init<<<1, 256, 0, (cudaStream_t)stream>>>(state, t_loc, t_scale, p_loc, p_scale, gather_idx, offset, D, B, S,
-                                                   max_aux, irec_device().ratio_len, omega, seed);
+                                                   max_aux, irec_ratio_len(), omega, seed);
     irec_count_launch();
     return irec_check_launch("k_gp_init");
 }
@@ -981,7 +981,7 @@ int irec_beam_step_score(void* state, int D, int B, int t, int64_t s_begin, int6
     if (workspace_bytes < irec_beam_step_workspace_bytes(D, B)) return irec_fail(IREC_E_CAPACITY, "beam_step_score: workspace too small");
     const BeamGeom g = make_geom(D);
     if (do_params) {
-        k_gp_params<<<std::max(1, std::min((g.DP + 255) / 256, 64)), 256, 0, s>>>(state, t, irec_device().d_ratio);
+        k_gp_params<<<std::max(1, std::min((g.DP + 255) / 256, 64)), 256, 0, s>>>(state, t, irec_ratio_tab());
         irec_count_launch();
     }
     const int grid_max = irec_device().sm_count * 4;
@@ -1140,7 +1140,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
             a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
             a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
-            a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
+            a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
             unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
             a.hist = reinterpret_cast<int2*>(w + 512);
             a.sched = reinterpret_cast<float*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux));
@@ -1176,8 +1176,8 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
         a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
         a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
         a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
-        a.out_sample = out_sample; a.T = irec_device().d_T; a.ratio_tab = irec_device().d_ratio;
-        a.ratio_len = irec_device().ratio_len;
+        a.out_sample = out_sample; a.T = irec_device().d_T; a.ratio_tab = irec_ratio_tab();
+        a.ratio_len = irec_ratio_len();
         a.hist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(workspace) + 256);
         a.work_counter = counter; a.DPmax = plan.DPmax; a.NC = plan.NC;
         launch_resident(plan, a, s);

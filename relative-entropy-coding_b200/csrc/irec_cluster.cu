@@ -436,7 +436,7 @@ int irec_launch_cluster(int G, const float* t_loc, const float* t_scale, const f
     a.gidx = gidx; a.offs = offs; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
     a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
     a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
-    a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
+    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     a.hist = hist; a.DPmax = make_geom(max_D).DP; a.NC = ((S * B + 31) / 32) * 32;
     a.order = order; a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab);
     a.G = G;

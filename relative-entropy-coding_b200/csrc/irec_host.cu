@@ -41,6 +41,13 @@ const IrecDevice& irec_device()
     return g_dev[d & 63];
 }
 
+// learned auxiliary ratios (rec/coding/coder.py:218-231): a per-thread override of the power-law table, installed by
+// irec_set_thread_aux_ratios for the calls that follow on the same host thread
+static thread_local const float* tl_ratio = nullptr;
+static thread_local int tl_ratio_len = 0;
+const float* irec_ratio_tab() { return tl_ratio ? tl_ratio : irec_device().d_ratio; }
+int irec_ratio_len() { return tl_ratio ? tl_ratio_len : irec_device().ratio_len; }
+
 // ---------------------------------------------------------------------------------------------
 // quantile table: TFP 0.9 special_math._ndtri in float32 (Cephes P0/Q0, P1/Q1, P2/Q2; Horner with
 // a separately rounded multiply and add per step), evaluated at p = float32(k) / float32(10007)
@@ -119,6 +126,14 @@ extern "C" {
 int irec_version(void) { return 100; }
 const char* irec_last_error_string(void) { return g_err; }
 int64_t irec_launch_count(void) { return g_launches.load(); }
+
+int irec_set_thread_aux_ratios(const float* dev_ratios, int n)
+{
+    if ((dev_ratios == nullptr) != (n == 0) || n < 0) return irec_fail(IREC_E_INVALID, "irec_set_thread_aux_ratios: need (ptr, n > 0) or (NULL, 0)");
+    tl_ratio = dev_ratios;
+    tl_ratio_len = n;
+    return IREC_OK;
+}
 
 float irec_aux_ratio(int i)
 {

@@ -419,7 +419,7 @@ static int is_block_common(bool encode, IsBlockArgs& a, int64_t max_block_dim, i
         return irec_fail(IREC_E_CUDA, "is block: stream table upload failed");
     if (cudaStreamSynchronize(s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "is block: sync failed");
     a.streams = reinterpret_cast<const TfStream*>(workspace);
-    a.ratio_tab = irec_device().d_ratio; a.ratio_len = irec_device().ratio_len;
+    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     const BeamGeom g = make_geom((int)max_block_dim);
     a.DPmax = g.DP;
     const size_t smem = sizeof(float) * 8 * (size_t)g.DP;

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "irec_init": (C.c_int, []),
     "irec_get_ndtri_table": (C.c_int, [_vp]),
     "irec_aux_ratio": (C.c_float, [_i32]),
+    "irec_set_thread_aux_ratios": (C.c_int, [_vp, _i32]),
     "irec_tf_op_seed": (C.c_int64, [_i64]),
     "irec_split_permutation": (C.c_int, [_i64, _i64, _vp]),
     "irec_beam_uniform_int": (C.c_int, [_i64, _i64, _i64, _vp, _vp]),
@@ -124,6 +125,27 @@ def tf_op_seed(seed):
 
 def aux_ratio(i):
     return float(load_library().irec_aux_ratio(int(i)))
+
+
+class thread_aux_ratios:
+    """`with thread_aux_ratios(table):` -- learned auxiliary variance ratios (a float32 CUDA tensor, or None for the
+    power law) for every libirec call made by this thread inside the block (include/irec.h: irec_set_thread_aux_ratios)."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def __enter__(self):
+        if self.table is not None:
+            if self.table.dtype != torch.float32 or self.table.dim() != 1 or self.table.numel() < 1:
+                raise NativeError("auxiliary ratio table must be a non-empty 1-D float32 CUDA tensor")
+            check(lib().irec_set_thread_aux_ratios(ptr(self.table), int(self.table.numel())), "irec_set_thread_aux_ratios")
+        return self
+
+    def __exit__(self, *exc):
+        if self.table is not None:
+            torch.cuda.current_stream().synchronize()      # the table is borrowed until the enqueued work has finished
+            check(load_library().irec_set_thread_aux_ratios(None, 0), "irec_set_thread_aux_ratios")
+        return False
 
 
 def split_permutation(n, seed):

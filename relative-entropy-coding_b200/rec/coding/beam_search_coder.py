@@ -35,12 +35,14 @@ class BeamSearchCoder(GaussianCoder):
         return torch.remainder((m * w).sum(dim=1, dtype=torch.int32), self.big_prime - 1) + 1
 
     def _encode_flat(self, tl, ts, pl, ps, gather, offsets, nb, max_dim, seed):
-        res = E.beam_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition, self.n_samples,
-                                   self.n_beams, seed)
+        with self._ratios_ctx(tl.device):
+            res = E.beam_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition, self.n_samples,
+                                       self.n_beams, seed)
         return res.indices, res.sample
 
     def _decode_flat(self, pl, ps, gather, offsets, nb, max_dim, seed, indices):
-        return E.beam_decode_blocks(pl, ps, gather, offsets, nb, self.n_samples, seed, indices)
+        with self._ratios_ctx(pl.device):
+            return E.beam_decode_blocks(pl, ps, gather, offsets, nb, self.n_samples, seed, indices)
 
     def encode_block(self, target_dist, coding_dist, seed, update_sampler=False, numpy=True):
         if target_dist.loc.shape[0] != 1:

@@ -8,8 +8,10 @@ layout, `CodingError` conditions, and the in-place reversal of the caller's inde
 counter-based (no global RNG is touched), whole tensors are coded by ONE kernel launch over all
 coder-blocks instead of a Python loop, and the `print`s of the reference are gone.
 
-Out of scope: learned auxiliary ratios (`extrapolate_auxiliary_ratios=False`,
-reference coder.py:233-410) and the rejection sampler.
+Learned auxiliary ratios (`extrapolate_auxiliary_ratios=False`, reference coder.py:197-410) are
+calibrated by `update_auxiliary_variance_ratios` (an offline SGD fit, torch autograd on the tensors' device) and then
+handed to the kernels as a device table (include/irec.h: irec_set_thread_aux_ratios) in place of the power law.
+Out of scope: the rejection sampler (its acceptance test draws unseeded uniforms, reference rejection_sampling.py:86-87).
 """
 import abc
 
@@ -142,33 +144,153 @@ class GaussianCoder(Coder):
         self.kl_per_partition = float(np.float32(kl_per_partition))      # reference :192 casts to float32
         self.extrapolate_auxiliary_ratios = extrapolate_auxiliary_ratios
         self._initialized = False
+        if not self.extrapolate_auxiliary_ratios:                        # reference :197-216
+            self.aux_variable_variance_ratios = np.array([1.], dtype=np.float32)
+            self.average_counts = np.array([1.], dtype=np.float32)
+        self._ratio_dev = {}                                             # device -> (version, table)
+        self._ratio_version = 0
 
     # -- ratios -----------------------------------------------------------------------------------
     def get_auxiliary_ratio(self, index):
+        """reference :218-231"""
         if self.extrapolate_auxiliary_ratios:
             return np.power(index + 1., AUX_RATIO_POWER_LAW)
-        raise CodingError("Coder has not been initialized yet, please call update_auxiliary_variance_ratios() first "
-                          "or use extrapolation (learned ratios are out of scope of the B200 hot path)")
-
-    def update_auxiliary_variance_ratios(self, *args, **kwargs):
-        raise NotImplementedError("learned auxiliary ratios (reference coder.py:233-410) are an offline calibration "
-                                  "step outside the accelerated path; use extrapolate_auxiliary_ratios=True")
+        if not self._initialized:
+            raise CodingError("Coder has not been initialized yet, please call"
+                              "update_auxiliary_variance_ratios() first"
+                              " or use extrapolation")
+        if index >= self.aux_variable_variance_ratios.shape[0]:
+            raise CodingError("KL divergence higher than auxiliary variables can account for. "
+                              "Update auxiliary variable ratios with high-enough KL divergence."
+                              "Maximum possible number of partitions is {}."
+                              "Requested {}".format(self.aux_variable_variance_ratios.shape[0], index + 1))
+        return self.aux_variable_variance_ratios[index]
 
     def _check_ratios(self):
         if not self.extrapolate_auxiliary_ratios:
             self.get_auxiliary_ratio(0)
+
+    def _ratios_ctx(self, device):
+        """context in which the kernels read this coder's ratio table (None = the library's power law)"""
+        if self.extrapolate_auxiliary_ratios:
+            return N.thread_aux_ratios(None)
+        self._check_ratios()
+        key = str(device)
+        cached = self._ratio_dev.get(key)
+        if cached is None or cached[0] != self._ratio_version:
+            cached = (self._ratio_version, torch.from_numpy(np.ascontiguousarray(self.aux_variable_variance_ratios,
+                                                                                 dtype=np.float32)).to(device))
+            self._ratio_dev[key] = cached
+        return N.thread_aux_ratios(cached[1])
+
+    def update_auxiliary_variance_ratios(self, target_dist, coding_dist, seed=42, **kwargs):
+        """reference :233-270: one calibration step from a (target, coder) pair; with block_size the tensors are split
+        with the coder's own permutation and every full block is a batch element (the last, short block is left out)"""
+        if self.extrapolate_auxiliary_ratios:
+            raise CodingError("update_auxiliary_variance_ratios needs extrapolate_auxiliary_ratios=False")
+        tl, ts = (torch.as_tensor(t, dtype=torch.float32) for t in (target_dist.loc, target_dist.scale))
+        pl, ps = (torch.as_tensor(t, dtype=torch.float32) for t in (coding_dist.loc, coding_dist.scale))
+        if self.block_size is None:
+            return self.update_block_auxiliary_variance_ratios(Normal(tl, ts), Normal(pl, ps), seed=seed, **kwargs)
+        n = tl.numel()
+        perm = N.split_permutation(n, seed).to(tl.device)
+        nfull = n // self.block_size if n % self.block_size else n // self.block_size - 1     # reference drops [-1] always
+        if nfull < 1:
+            raise CodingError("update_auxiliary_variance_ratios: need at least two blocks (the last one is left out)")
+        take = perm[:nfull * self.block_size]
+        stack = lambda t: t.reshape(-1)[take].reshape(nfull, self.block_size)                  # noqa: E731
+        return self.update_block_auxiliary_variance_ratios(Normal(stack(tl), stack(ts)), Normal(stack(pl), stack(ps)),
+                                                           seed=seed, **kwargs)
+
+    def update_block_auxiliary_variance_ratios(self, target_dist, coding_dist, relative_tolerance=1e-4, max_iters=10000,
+                                               learning_rate=0.001, seed=42):
+        """reference :272-410.  For ratio = max .. 2 (number of auxiliary variables still to go): SGD on one scalar
+        (sigmoid-reparametrised variance ratio) so that the auxiliary variable carries at most Omega nats and leaves at
+        most Omega * (ratio - 1); running average over calls; then condition target and coder on a draw of the auxiliary
+        variable and continue.  The reference draws that sample from TF's global RNG; here a torch.Generator seeded with
+        `seed` (no global state is touched)."""
+        if self.extrapolate_auxiliary_ratios:
+            raise CodingError("update_block_auxiliary_variance_ratios needs extrapolate_auxiliary_ratios=False")
+        t_loc, t_scale = (torch.as_tensor(t, dtype=torch.float32).detach().clone() for t in (target_dist.loc, target_dist.scale))
+        c_loc, c_scale = (torch.as_tensor(t, dtype=torch.float32).detach().clone() for t in (coding_dist.loc, coding_dist.scale))
+        dev = t_loc.device
+        dims = tuple(range(1, t_loc.dim()))
+        omega = self.kl_per_partition
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed))
+
+        def kl(ql, qs, pl_, ps_):
+            dl = torch.log(qs) - torch.log(ps_)
+            return (0.5 * ((ql - pl_) / ps_) ** 2 + 0.5 * torch.expm1(2. * dl) - dl).sum(dim=dims)
+
+        total_kl = kl(t_loc, t_scale, c_loc, c_scale)
+        num_aux = 1 + torch.floor(total_kl / omega).to(torch.int32)
+        max_num = int(num_aux.max())
+        cur = self.aux_variable_variance_ratios.shape[0]
+        if max_num > cur:
+            grown = np.zeros(max_num, dtype=np.float32); grown[:cur] = self.aux_variable_variance_ratios
+            counts = np.zeros(max_num, dtype=np.float32); counts[:cur] = self.average_counts
+            self.aux_variable_variance_ratios, self.average_counts = grown, counts
+        ratios, counts = self.aux_variable_variance_ratios, self.average_counts
+        for ratio in range(max_num, 1, -1):
+            sel = (num_aux >= ratio).nonzero().reshape(-1)
+            n_el = int(sel.numel())
+            tl, ts, cl, cs = t_loc[sel], t_scale[sel], c_loc[sel], c_scale[sel]
+            tot = kl(tl, ts, cl, cs)
+            if ratios[ratio - 1] > 0.:
+                init = float(ratios[ratio - 1])
+            elif ratio < max_num:
+                init = float(ratios[ratio])
+            else:
+                init = 1. / ratio
+            init = min(max(init, 1e-10), 1. - 1e-10)                     # sigmoid_inverse, reference :19-25
+            param = torch.tensor(np.log(init) - np.log1p(-init), dtype=torch.float32, device=dev, requires_grad=True)
+            prev_loss = np.inf
+            tgt, cod = Normal(tl, ts), Normal(cl, cs)
+            for _ in range(int(max_iters)):
+                r = torch.sigmoid(param)
+                aux_var = r * cs * cs
+                aux_t = get_auxiliary_target(tgt, cod, aux_var)
+                aux_c = get_auxiliary_coder(cod, aux_var)
+                aux_kl = kl(aux_t.loc, aux_t.scale, aux_c.loc, aux_c.scale)
+                rest = tot - aux_kl
+                loss = (torch.where(aux_kl > omega, (aux_kl - omega) ** 2, torch.zeros_like(aux_kl)) +
+                        torch.where(rest > omega * (ratio - 1), (rest - omega * (ratio - 1)) ** 2,
+                                    torch.zeros_like(rest))).mean()
+                grad, = torch.autograd.grad(loss, param)
+                with torch.no_grad():
+                    param -= learning_rate * grad
+                loss_v = float(loss.detach())
+                if abs(prev_loss - loss_v) < relative_tolerance:
+                    break
+                prev_loss = loss_v
+            with torch.no_grad():
+                r_fit = float(r.detach())
+                ratios[ratio - 1] = (ratios[ratio - 1] * counts[ratio - 1] + r_fit * n_el) / (counts[ratio - 1] + n_el)
+                counts[ratio - 1] += n_el
+                aux_var = float(ratios[ratio - 1]) * cs * cs
+                aux_t = Normal(aux_t.loc.detach(), aux_t.scale.detach())     # of the last SGD iterate, as the reference
+                sample = aux_t.loc + aux_t.scale * torch.randn(aux_t.loc.shape, generator=gen, device=dev)
+                new_t = get_conditional_target(tgt, cod, aux_var, sample)
+                new_c = get_conditional_coder(cod, aux_var, sample)
+                t_loc[sel], t_scale[sel] = new_t.loc, new_t.scale
+                c_loc[sel], c_scale[sel] = new_c.loc, new_c.scale
+        self._initialized = True
+        self._ratio_version += 1
 
     # -- sampler dispatch -------------------------------------------------------------------------
     def _fused_importance(self):
         return isinstance(self.sampler, ImportanceSampler) and np.isinf(self.sampler.alpha)
 
     def _encode_flat(self, tl, ts, pl, ps, gather, offsets, nb, max_dim, seed):
-        indices, sample = E.is_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition,
-                                             self.sampler.n_samples, seed)
+        with self._ratios_ctx(tl.device):
+            indices, sample = E.is_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition,
+                                                 self.sampler.n_samples, seed)
         return indices, sample
 
     def _decode_flat(self, pl, ps, gather, offsets, nb, max_dim, seed, indices):
-        return E.is_decode_blocks(pl, ps, gather, offsets, nb, max_dim, seed, indices)
+        with self._ratios_ctx(pl.device):
+            return E.is_decode_blocks(pl, ps, gather, offsets, nb, max_dim, seed, indices)
 
     # -- whole tensors ----------------------------------------------------------------------------
     def encode(self, target_dist, coding_dist, seed, **kwargs):
