@@ -70,6 +70,10 @@ int irec_split_permutation(int64_t n, int64_t seed, int64_t* perm_out);
  *   irec_is_normal_stream : z[j] of Normal(0,1).sample after set_seed(seed) (importance_sampling.py:38,54) */
 int irec_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out, void* stream);
 int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, void* stream);
+/*   irec_normal_stream_seeded : z[j] of tf.random.normal(..., seed=op_seed) after set_seed(global_seed), i.e.
+ *   tfd.Normal.sample(n, seed=op_seed) before scale/shift -- the candidate buffers of the rejection sampler's
+ *   NaiveSampleGenerator (rec/coding/sample_generator.py:53-66) */
+int irec_normal_stream_seeded(int64_t global_seed, int64_t op_seed, int64_t start, int64_t n, float* out, void* stream);
 
 /* KL(target || coder) summed per block and n_aux = ceil(KL / omega)
  * (rec/coding/coder.py:499-501, beam_search_coder.py:57-59).  out_kl/out_n_aux: [nb]. */

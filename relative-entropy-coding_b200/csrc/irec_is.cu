@@ -358,6 +358,16 @@ int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, vo
     return irec_check_launch("k_is_normal_stream");
 }
 
+int irec_normal_stream_seeded(int64_t global_seed, int64_t op_seed, int64_t start, int64_t n, float* out, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (n <= 0) return IREC_OK;
+    k_is_normal_stream<<<(int)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, (cudaStream_t)stream>>>(
+        tf_stream_seeded(global_seed, op_seed), start, n, out);
+    irec_count_launch();
+    return irec_check_launch("k_is_normal_stream");
+}
+
 size_t irec_is_workspace_bytes(int D)
 {
     if (irec_init() != IREC_OK) return 0;

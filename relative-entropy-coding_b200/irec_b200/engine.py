@@ -211,6 +211,14 @@ def is_normal_stream(seed, start, n, device="cuda"):
     return out
 
 
+def normal_stream_seeded(global_seed, op_seed, start, n, device="cuda"):
+    """z[start : start + n] of tf.random.normal(seed=op_seed) after tf.random.set_seed(global_seed)"""
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    N.check(N.lib().irec_normal_stream_seeded(int(global_seed), int(op_seed), int(start), int(n), N.ptr(out), N.stream_ptr()),
+            "irec_normal_stream_seeded")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # candidate-range sharded beam coder for ONE block (large S; 1..8 GPUs).  Every rank holds a replica
 # of the block state; per partition each rank scores its contiguous candidate range, the per-rank

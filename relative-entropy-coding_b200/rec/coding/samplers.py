@@ -63,21 +63,54 @@ class ImportanceSampler(Sampler):
 
 
 class RejectionSampler(Sampler):
-    """Out of scope of the B200 hot path (reference samplers.py:104-177,
-    rejection_sampling.py, sample_generator.py).  Present so that imports of the reference's names work."""
+    """reference samplers.py:104-177 -- buffered rejection sampler with an empirical index code.  Host-side logic (torch /
+    NumPy float64), candidates regenerated on the GPU; see rejection_sampling.py for the two places where the
+    reference's unseeded draws are replaced by seeded ones."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("RejectionSampler is outside the accelerated iREC path; use ImportanceSampler or "
-                                  "BeamSearchCoder")
+    def __init__(self, sample_buffer_size, r_buffer_size, use_pseudo_sampler=False, name="rejection_sampler", **kwargs):
+        super().__init__(name=name, **kwargs)
+        from rec.coding.sample_generator import NaiveSampleGenerator
+        if use_pseudo_sampler:
+            raise NotImplementedError("PseudoSampleGenerator (reference sample_generator.py:69-133) is not built")
+        self.sample_buffer_size = int(sample_buffer_size)
+        self.r_buffer_size = int(r_buffer_size)
+        self.sample_generator = NaiveSampleGenerator(self.sample_buffer_size)
+        self.average_count = 0.
+        self._initialized = False
+        self.acceptance_probabilities = np.zeros(self.r_buffer_size, dtype=np.float64)
+        self.spillover_probability = 0.
+        self.spillover_acceptance_probability = 0.
 
-    def coded_sample(self, target, coder, seed):
-        raise NotImplementedError
-
-    def decode_sample(self, coder, sample_index, seed):
-        raise NotImplementedError
+    def update(self, target, coder, seed=0):
+        """running average of the per-index acceptance probabilities (reference :136-149)"""
+        from rec.coding.rejection_sampling import get_r_pstar, get_t_p_mass
+        log_ratios, t_mass, p_mass = get_t_p_mass(target, coder, seed=seed + int(self.average_count))
+        _, pstar = get_r_pstar(log_ratios, t_mass, p_mass, self.r_buffer_size, dtype=np.float64)
+        acc = pstar - np.concatenate(([0.], pstar[:-1]))
+        self.acceptance_probabilities = (self.acceptance_probabilities * self.average_count + acc) / (self.average_count + 1.)
+        self.average_count += 1.
+        self.spillover_probability = 1. - float(np.sum(self.acceptance_probabilities))
+        self.spillover_acceptance_probability = float(self.acceptance_probabilities[-1] /
+                                                      (1. - np.sum(self.acceptance_probabilities[:-1])))
+        self._initialized = True
 
     def get_codelength(self, index):
-        raise NotImplementedError
+        """nats (reference :151-159)"""
+        assert self._initialized
+        index = int(index)
+        if index < self.r_buffer_size:
+            return float(-np.log(self.acceptance_probabilities[index]))
+        return float(-(np.log(self.spillover_probability) +
+                       np.log(1. - self.spillover_acceptance_probability) * (index - self.r_buffer_size) +
+                       np.log(self.spillover_acceptance_probability)))
 
-    def update(self, target, coder):
-        raise NotImplementedError
+    def coded_sample(self, target, coder, seed):
+        from rec.coding.rejection_sampling import gaussian_rejection_sample_small
+        return gaussian_rejection_sample_small(t_dist=target, p_dist=coder, sample_buffer_size=self.sample_buffer_size,
+                                               r_buffer_size=self.r_buffer_size, sample_generator=self.sample_generator,
+                                               seed=int(seed))
+
+    def decode_sample(self, coder, sample_index, seed):
+        sample_index = int(sample_index)
+        return self.sample_generator.generate_index(sample_index % self.sample_buffer_size, coder,
+                                                    seed=int(seed) + sample_index // self.sample_buffer_size)

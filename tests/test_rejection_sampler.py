@@ -1,0 +1,118 @@
+"""The rejection sampler (reference rec/coding/rejection_sampling.py, sample_generator.py,
+samplers.py:104-177).  The tests mirror the reference's own: rec/coding/tests/test_rejection_sampling.py (closed-form
+r / p* buffers against the step-by-step recursion), test_samplers.py (positive log-ratio of coded samples, decode ==
+encode, code lengths sum to one) and test_sample_generator.py (generate_index == get_index)."""
+import numpy as np
+import pytest
+import torch
+
+from rec.coding.rejection_sampling import get_r_pstar
+
+
+def _masses(n_samples, oversampling, seed=0):
+    """get_t_p_mass (reference :11-24) in NumPy for t = N(3, 0.001), p = N(0, 1)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = n_samples * oversampling
+    y = (3. + 0.001 * rng.standard_normal(n)).astype(np.float32)
+    lp_t = -0.5 * ((y - 3.) / 0.001) ** 2 - (0.5 * np.log(2 * np.pi) + np.log(0.001))
+    lp_p = -0.5 * y ** 2 - 0.5 * np.log(2 * np.pi)
+    t_mass = np.full(n, -np.log(n_samples), np.float32)
+    p_mass = (-np.log(n_samples) + lp_p - lp_t).astype(np.float32)
+    lr = t_mass - p_mass
+    ind = np.argsort(lr, kind="stable")[oversampling // 2::oversampling]
+    return lr[ind], t_mass[ind], p_mass[ind]
+
+
+def _baseline(log_ratios, t_mass, p_mass, r_buffer_size):
+    """the slow recursion of the reference's test (test_rejection_sampling.py:12-30)"""
+    ratios = np.exp(log_ratios)
+    t_cum = np.exp(np.logaddexp.accumulate(t_mass.astype(np.float64)))
+    p_cum_all = np.exp(np.logaddexp.accumulate(p_mass.astype(np.float64)))
+    p_zero = float(1. - np.exp(np.logaddexp.reduce(p_mass.astype(np.float64))))
+    r_buf, ps_buf = np.zeros(r_buffer_size), np.zeros(r_buffer_size)
+    r, pstar, r_ind = 0., 0., 0
+    for i in range(r_buffer_size):
+        r += 1. - pstar
+        r_buf[i] = r
+        while ratios[r_ind] < r:
+            r_ind += 1
+        p_cum = p_zero + (p_cum_all[r_ind - 1] if r_ind > 0 else 0.)
+        t_c = t_cum[r_ind - 1] if r_ind > 0 else 0.
+        pstar = (1. - p_cum) * r + t_c
+        ps_buf[i] = pstar
+    return r_buf, ps_buf
+
+
+@pytest.mark.parametrize("n_samples,size,atol", [(10, 10000, 0.), (2, 100000, 1e-5)])
+def test_r_pstar_closed_form_matches_recursion(n_samples, size, atol):
+    lr, tm, pm = _masses(n_samples, 10)
+    r, ps = get_r_pstar(lr, tm, pm, r_buffer_size=size, dtype=np.float64)
+    rb, psb = _baseline(lr, tm, pm, size)
+    np.testing.assert_allclose(r, rb, rtol=1e-5, atol=atol)
+    np.testing.assert_allclose(ps, psb, rtol=1e-5, atol=atol)
+    assert np.all(np.diff(ps) >= -1e-12) and ps[-1] <= 1. + 1e-9          # accepted mass is a CDF
+
+
+@pytest.fixture(scope="module")
+def cuda(built):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda:0"
+
+
+@pytest.mark.gpu
+def test_sampler_logprob_decode_codelength(cuda):
+    from irec_b200 import Normal
+    from rec.coding.samplers import RejectionSampler
+    from rec.coding.sample_generator import normal_log_prob
+    sampler = RejectionSampler(sample_buffer_size=10000, r_buffer_size=10000)
+    t = Normal(np.full((1, 1, 1), 2., np.float32), np.full((1, 1, 1), 0.01, np.float32), device=cuda)
+    p = Normal(np.zeros((1, 1, 1), np.float32), np.ones((1, 1, 1), np.float32), device=cuda)
+    gains = []
+    for k in range(5):
+        index, sample = sampler.coded_sample(t, p, seed=42069 + k)
+        gains.append(float((normal_log_prob(sample, t.loc, t.scale) - normal_log_prob(sample, p.loc, p.scale)).sum()))
+        rec = sampler.decode_sample(p, index, seed=42069 + k)
+        assert torch.equal(rec, sample)                                     # reference: assert_allclose; here bit-exact
+    assert np.mean(gains) > 0.
+    again = sampler.coded_sample(t, p, seed=42069)
+    first = sampler.coded_sample(t, p, seed=42069)
+    assert again[0] == first[0] and torch.equal(again[1], first[1])        # a function of (inputs, seed)
+    sampler.update(t, p)
+    sampler.update(t, p)
+    assert abs(float(np.sum(sampler.acceptance_probabilities)) + sampler.spillover_probability - 1.) < 1e-6
+    assert np.isfinite(sampler.get_codelength(again[0])) and sampler.get_codelength(again[0]) > 0.
+
+
+@pytest.mark.gpu
+def test_generate_index_matches_buffer(cuda):
+    """reference test_sample_generator.py:18-23"""
+    from irec_b200 import Normal
+    from rec.coding.sample_generator import NaiveSampleGenerator
+    gen = NaiveSampleGenerator(100)
+    rng = np.random.Generator(np.random.PCG64(1))
+    t = Normal(rng.standard_normal((1, 5, 3)).astype(np.float32), np.exp(rng.standard_normal((1, 5, 3))).astype(np.float32), device=cuda)
+    p = Normal(rng.standard_normal((1, 5, 3)).astype(np.float32), np.exp(rng.standard_normal((1, 5, 3))).astype(np.float32), device=cuda)
+    ratios = gen.get_ratios(t, p, seed=7)
+    assert ratios.shape == (100,)
+    for i in (0, 1, 57, 99):
+        assert torch.equal(gen.get_index(i), gen.generate_index(i, p, seed=7))
+
+
+@pytest.mark.gpu
+def test_gaussian_coder_with_rejection_sampler_round_trip(cuda):
+    """GaussianCoder's auxiliary-variable loop (coder.py:493-584) with the rejection sampler plugged in"""
+    from irec_b200 import Normal
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import RejectionSampler
+    rng = np.random.Generator(np.random.PCG64(3))
+    D = 24
+    mu = (0.8 * rng.standard_normal((1, D))).astype(np.float32)
+    sig = np.exp(rng.uniform(-1., 0., (1, D))).astype(np.float32)
+    t = Normal(mu, sig, device=cuda)
+    p = Normal(np.zeros((1, D), np.float32), np.ones((1, D), np.float32), device=cuda)
+    coder = GaussianCoder(kl_per_partition=4., sampler=RejectionSampler(sample_buffer_size=2000, r_buffer_size=20000))
+    indices, sample = coder.encode(t, p, seed=11)
+    assert len(indices) >= 2
+    decoded = coder.decode(p, [int(i) for i in indices], seed=11)
+    assert torch.allclose(decoded, sample, rtol=0., atol=1e-5)             # conditioning arithmetic replayed in float32
