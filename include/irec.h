@@ -74,6 +74,11 @@ int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, vo
  *   tfd.Normal.sample(n, seed=op_seed) before scale/shift -- the candidate buffers of the rejection sampler's
  *   NaiveSampleGenerator (rec/coding/sample_generator.py:53-66) */
 int irec_normal_stream_seeded(int64_t global_seed, int64_t op_seed, int64_t start, int64_t n, float* out, void* stream);
+/* HOST (tests): the table-driven float64 log / sincos behind the Box-Muller candidates (csrc/irec_boxmuller.cuh),
+ * evaluated on the host with the operation sequence of the device, for m[i] = the 23 mantissa bits of a Philox word:
+ * logf_out = float(log(max(Uint32ToFloat(m), 1e-7f))), (sin_out, cos_out) = float(sin/cos(float(2 pi Uint32ToFloat(m)))).
+ * Any output pointer may be NULL.  Used to check ALL 2^23 arguments against the float64-libm definition. */
+int irec_bm_components_host(const uint32_t* m, int64_t n, float* logf_out, float* sin_out, float* cos_out);
 
 /* KL(target || coder) summed per block and n_aux = ceil(KL / omega)
  * (rec/coding/coder.py:499-501, beam_search_coder.py:57-59).  out_kl/out_n_aux: [nb]. */

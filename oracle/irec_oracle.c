@@ -205,6 +205,20 @@ static void box_muller(uint32_t x0, uint32_t x1, float* f0, float* f1)
     *f1 = c * u2;
 }
 
+/* the three float32 functions behind box_muller, by definition (float64 libm, round once), for m = 23 mantissa bits */
+void orc_bm_components(const uint32_t* m, int64_t n, float* logf_out, float* sin_out, float* cos_out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const float u = u32_to_float(m[i]);
+        float u1 = u;
+        if (u1 < 1.0e-7f) u1 = 1.0e-7f;
+        const float v1 = (float)(2.0 * 3.14159265358979323846 * (double)u);
+        if (logf_out) logf_out[i] = c_logf(u1);
+        if (sin_out) sin_out[i] = (float)sin((double)v1);
+        if (cos_out) cos_out[i] = (float)cos((double)v1);
+    }
+}
+
 static float tf_stream_normal(int64_t s1, int64_t s2, uint64_t j)
 {
     uint64_t g = j >> 2;

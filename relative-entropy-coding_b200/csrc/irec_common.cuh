@@ -107,6 +107,20 @@ __device__ __forceinline__ float u32_to_float(uint32_t x)
 __device__ __forceinline__ float c_logf(float x) { return (float)log((double)x); }
 
 // TF random_distributions.h BoxMullerFloat (v1 = float(2.0f * M_PI(double) * u))
+#ifdef IREC_BM_TABLES          // irec_is.cu: table-driven float64 log / sincos (irec_boxmuller.cuh), same float32 results
+__device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& f0, float& f1)
+{
+    float u1 = u32_to_float(x0);
+    if (u1 < 1.0e-7f) u1 = 1.0e-7f;
+    const float v1 = (float)(6.283185307179586 * (double)u32_to_float(x1));
+    const BmTables t = IREC_BM_TABLES;
+    const float u2 = __fsqrt_rn(__fmul_rn(-2.0f, bm_logf(u1, t)));
+    float s, c;
+    bm_sincosf(v1, t, s, c);
+    f0 = __fmul_rn(s, u2);
+    f1 = __fmul_rn(c, u2);
+}
+#else
 __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& f0, float& f1)
 {
     float u1 = u32_to_float(x0);
@@ -118,6 +132,7 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& f0, 
     f0 = __fmul_rn((float)sd, u2);
     f1 = __fmul_rn((float)cd, u2);
 }
+#endif
 
 // 4 consecutive N(0,1) stream elements of an ALIGNED group
 __device__ __forceinline__ float4 tf_normal_group(const TfStream& st, uint64_t g)

@@ -8,8 +8,18 @@
 // j = s*D + d.  Canonical score of sample s:  sum_d (A d + E) d,  d = z - mu',  A = 0.5 (1 - 1/sigma'^2),
 // E = mu'  (= log N(z; mu', sigma') - log N(z; 0, 1) up to a constant), 32-dim chunk sums combined by a
 // pairwise tree -- the same reduction contract as the beam path.
+#include <string.h>
+#include "irec_boxmuller.cuh"
+// device copies of the Box-Muller tables (filled once per device by bm_ensure_tables)
+__device__ double2 g_bm_logA[128];
+__device__ double2 g_bm_logB[128];
+__device__ double2 g_bm_sc[257];
+#ifndef IREC_BM_LIBM            // -DIREC_BM_LIBM: the libm-grade log()/sincos() path (A/B runs)
+#define IREC_BM_TABLES (BmTables{ g_bm_logA, g_bm_logB, g_bm_sc })
+#endif
 #include "irec_beam.cuh"
 #include "irec_host.h"
+#include <mutex>
 
 // per-lane chunk sum: 32 dims starting at chunk's first dim; A4/M4 in CI layout (q0 = first quad index)
 __device__ __forceinline__ float is_score_chunk(const float4* __restrict__ A4, const float4* __restrict__ M4, int P, int q0,
@@ -347,11 +357,82 @@ __global__ void __launch_bounds__(256) k_is_block(const IsBlockArgs a)
 // =============================================================================================
 static TfStream is_stream_for_seed(int64_t seed) { return tf_stream_seeded(seed, irec_tf_op_seed(seed)); }
 
+// ---- Box-Muller tables (irec_boxmuller.cuh): built in long double on the host, one upload per device ----
+static double2 h_bm_logA[128], h_bm_logB[128], h_bm_sc[257];
+static std::once_flag bm_host_once;
+static void bm_build_host_tables()
+{
+    for (int j = 0; j < 128; ++j) {
+        const long double c = 1.0L + ((long double)j + 0.5L) / 128.0L;
+        const double invA = (double)(1.0L / c), invB = (double)(2.0L / c);
+        h_bm_logA[j] = make_double2(invA, (double)(-logl((long double)invA)));
+        h_bm_logB[j] = make_double2(invB, (double)(-logl((long double)invB)));
+    }
+    h_bm_logB[127] = make_double2(1.0, 0.0);                 // arguments next to 1: r = m - 1 exactly, no table term
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int j = 0; j <= 256; ++j) {
+        const long double a = (long double)j * pi / 128.0L;
+        h_bm_sc[j] = make_double2((double)sinl(a), (double)cosl(a));
+    }
+    const double q[5][2] = { { 0, 1 }, { 1, 0 }, { 0, -1 }, { -1, 0 }, { 0, 1 } };     // exact at multiples of pi/2
+    for (int k = 0; k < 5; ++k) h_bm_sc[64 * k] = make_double2(q[k][0], q[k][1]);
+}
+static BmTables bm_host_tables()
+{
+    std::call_once(bm_host_once, bm_build_host_tables);
+    return BmTables{ h_bm_logA, h_bm_logB, h_bm_sc };
+}
+static int bm_ensure_tables()
+{
+    static std::mutex mu;
+    static bool done[64] = { false };
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return irec_fail(IREC_E_CUDA, "bm_ensure_tables: no CUDA device");
+    if (done[d]) return IREC_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[d]) return IREC_OK;
+    bm_host_tables();
+    if (cudaMemcpyToSymbol(g_bm_logA, h_bm_logA, sizeof(h_bm_logA)) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_bm_logB, h_bm_logB, sizeof(h_bm_logB)) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_bm_sc, h_bm_sc, sizeof(h_bm_sc)) != cudaSuccess)
+        return irec_fail(IREC_E_CUDA, "bm_ensure_tables: table upload failed");
+    done[d] = true;
+    return IREC_OK;
+}
+#define IREC_ENSURE_BM()                          \
+    do {                                          \
+        const int rc_bm_ = bm_ensure_tables();    \
+        if (rc_bm_ != IREC_OK) return rc_bm_;     \
+    } while (0)
+
 extern "C" {
+
+int irec_bm_components_host(const uint32_t* m, int64_t n, float* logf_out, float* sin_out, float* cos_out)
+{
+    // HOST evaluation of the device's table-driven functions (same IEEE operation sequence), for exhaustive checks:
+    // logf_out[i] = bm_logf(Uint32ToFloat(m[i]) clamped), (sin_out, cos_out)[i] = bm_sincosf(float(2 pi Uint32ToFloat(m[i])))
+    const BmTables t = bm_host_tables();
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t b = 0x3F800000u | (m[i] & 0x7FFFFFu);
+        float f;
+        memcpy(&f, &b, 4);
+        const float u = f - 1.0f;
+        float u1 = u;
+        if (u1 < 1.0e-7f) u1 = 1.0e-7f;
+        if (logf_out) logf_out[i] = bm_logf(u1, t);
+        const float v1 = (float)(6.283185307179586 * (double)u);
+        float s, c;
+        bm_sincosf(v1, t, s, c);
+        if (sin_out) sin_out[i] = s;
+        if (cos_out) cos_out[i] = c;
+    }
+    return IREC_OK;
+}
 
 int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     if (n <= 0) return IREC_OK;
     k_is_normal_stream<<<(int)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, (cudaStream_t)stream>>>(is_stream_for_seed(seed), start, n, out);
     irec_count_launch();
@@ -361,6 +442,7 @@ int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, vo
 int irec_normal_stream_seeded(int64_t global_seed, int64_t op_seed, int64_t start, int64_t n, float* out, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     if (n <= 0) return IREC_OK;
     k_is_normal_stream<<<(int)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, (cudaStream_t)stream>>>(
         tf_stream_seeded(global_seed, op_seed), start, n, out);
@@ -381,6 +463,7 @@ int irec_is_coded_sample(const float* t_loc, const float* t_scale, const float* 
                          void* workspace, size_t workspace_bytes, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     cudaStream_t s = (cudaStream_t)stream;
     if (D <= 0 || S <= 0) return irec_fail(IREC_E_INVALID, "is_coded_sample: bad sizes");
     if (workspace_bytes < irec_is_workspace_bytes(D)) return irec_fail(IREC_E_CAPACITY, "is_coded_sample: workspace too small");
@@ -407,6 +490,7 @@ int irec_is_decode_sample(const float* p_loc, const float* p_scale, int D, const
                           float* out_sample, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     if (D <= 0) return irec_fail(IREC_E_INVALID, "is_decode_sample: bad sizes");
     k_is_decode_sample<<<std::max(1, std::min((D + 255) / 256, 256)), 256, 0, (cudaStream_t)stream>>>(
         p_loc, p_scale, D, index, is_stream_for_seed(seed), out_sample);
@@ -454,6 +538,7 @@ int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc,
                    float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     if (nb <= 0) return IREC_OK;
     if (S <= 0 || !(omega > 0.f)) return irec_fail(IREC_E_INVALID, "is_encode: bad arguments");
     IsBlockArgs a{};
@@ -469,6 +554,7 @@ int irec_is_decode(const float* p_loc, const float* p_scale, const int64_t* gath
                    float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
 {
     IREC_ENSURE_INIT();
+    IREC_ENSURE_BM();
     if (nb <= 0) return IREC_OK;
     IsBlockArgs a{};
     a.p_loc = p_loc; a.p_scale = p_scale; a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb;
