@@ -23,11 +23,31 @@ struct BmTables {
     const double2* sc;     // [257] (sin, cos)(j * pi / 128), exact 0 / +-1 at multiples of pi/2
 };
 
-#define BM_SQRT2 1.4142135623730951
-#define BM_LN2 0.6931471805599453
-#define BM_H_HI 0.024543692605220713     /* pi/128 with the low 21 significand bits cleared (31 bits): j * H_HI is exact for j <= 256 */
-#define BM_H_LO 9.495469541415925e-13    /* pi/128 - H_HI */
-#define BM_INV_H 40.74366543152521       /* 128/pi */
+// Every float64 constant lives in one array: in constant memory on the device (a DFMA takes a c[bank][offset] operand;
+// as immediates each constant costs two UMOVs per use -- 35 extra instructions per pair of normals), a static table on
+// the host.
+#define BM_NK 24
+#define BM_K_INIT { 1.4142135623730951,       /* 0  sqrt 2 */                                                   \
+                    0.6931471805599453,       /* 1  ln 2 */                                                     \
+                    0.024543692605220713,     /* 2  H_HI = pi/128 with the low 21 significand bits cleared (31 bits): j * H_HI is exact for j <= 256 */ \
+                    9.495469541415925e-13,    /* 3  H_LO = pi/128 - H_HI */                                      \
+                    40.74366543152521,        /* 4  128/pi */                                                   \
+                    1.0 / 9.0, -1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5,   /* 5..12 log1p */ \
+                    1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0,                                   /* 13..16 sin */  \
+                    1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5,                           /* 17..21 cos */  \
+                    0.0, 0.0 }
+static __constant__ double c_bm_k[BM_NK] = BM_K_INIT;
+static const double bm_k_host[BM_NK] = BM_K_INIT;
+#ifdef __CUDA_ARCH__
+#define BM_K(i) c_bm_k[i]
+#else
+#define BM_K(i) bm_k_host[i]
+#endif
+#define BM_SQRT2 BM_K(0)
+#define BM_LN2 BM_K(1)
+#define BM_H_HI BM_K(2)
+#define BM_H_LO BM_K(3)
+#define BM_INV_H BM_K(4)
 
 #ifdef __CUDA_ARCH__
 #define BM_FMA(a, b, c) __fma_rn((a), (b), (c))
@@ -70,13 +90,13 @@ __host__ __device__ __forceinline__ float bm_logf(float u1, const BmTables& t)
     else tv = BM_LD(t.logA + j);
     const double r = BM_FMA(m, tv.x, -1.0);                            // |r| <= 2^-7, exact up to one rounding
     // log1p(r) = r - r^2/2 + r^3/3 - ... + r^9/9   (next term < 2^-73)
-    double p = BM_FMA(r, 1.0 / 9.0, -1.0 / 8.0);
-    p = BM_FMA(p, r, 1.0 / 7.0);
-    p = BM_FMA(p, r, -1.0 / 6.0);
-    p = BM_FMA(p, r, 1.0 / 5.0);
-    p = BM_FMA(p, r, -1.0 / 4.0);
-    p = BM_FMA(p, r, 1.0 / 3.0);
-    p = BM_FMA(p, r, -0.5);
+    double p = BM_FMA(r, BM_K(5), BM_K(6));
+    p = BM_FMA(p, r, BM_K(7));
+    p = BM_FMA(p, r, BM_K(8));
+    p = BM_FMA(p, r, BM_K(9));
+    p = BM_FMA(p, r, BM_K(10));
+    p = BM_FMA(p, r, BM_K(11));
+    p = BM_FMA(p, r, BM_K(12));
     p = BM_MUL(p, BM_MUL(r, r));
     p = BM_ADD(p, r);
     const double base = BM_FMA((double)e, BM_LN2, tv.y);               // e == 0 and tv.y == 0 next to 1: exact
@@ -92,14 +112,14 @@ __host__ __device__ __forceinline__ void bm_sincosf(float v1, const BmTables& t,
     double x = BM_FMA(-jd, BM_H_HI, v);                                // exact
     x = BM_FMA(-jd, BM_H_LO, x);                                       // |x| <= pi/256 (+ rounding of the index)
     const double z = BM_MUL(x, x);
-    double ps = BM_FMA(z, 1.0 / 362880.0, -1.0 / 5040.0);
-    ps = BM_FMA(ps, z, 1.0 / 120.0);
-    ps = BM_FMA(ps, z, -1.0 / 6.0);
+    double ps = BM_FMA(z, BM_K(13), BM_K(14));
+    ps = BM_FMA(ps, z, BM_K(15));
+    ps = BM_FMA(ps, z, BM_K(16));
     const double sx = BM_FMA(BM_MUL(ps, z), x, x);                     // sin x
-    double pc = BM_FMA(z, 1.0 / 3628800.0, -1.0 / 40320.0);
-    pc = BM_FMA(pc, z, 1.0 / 720.0);
-    pc = BM_FMA(pc, z, -1.0 / 24.0);
-    pc = BM_FMA(pc, z, 0.5);
+    double pc = BM_FMA(z, BM_K(17), BM_K(18));
+    pc = BM_FMA(pc, z, BM_K(19));
+    pc = BM_FMA(pc, z, BM_K(20));
+    pc = BM_FMA(pc, z, BM_K(21));
     const double cx = BM_FMA(-pc, z, 1.0);                             // cos x
     const double2 sc = BM_LD(t.sc + j);
     s = BM_D2F(BM_FMA(sc.x, cx, BM_MUL(sc.y, sx)));

@@ -200,7 +200,7 @@ struct IsBlockArgs {
 };
 
 template <bool ENCODE>
-__global__ void __launch_bounds__(256) k_is_block(const IsBlockArgs a)
+__global__ void __launch_bounds__(256, 3) k_is_block(const IsBlockArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_kl[IS_MAX_D / 32];
@@ -517,7 +517,8 @@ static int is_block_common(bool encode, IsBlockArgs& a, int64_t max_block_dim, i
     const BeamGeom g = make_geom((int)max_block_dim);
     a.DPmax = g.DP;
     const size_t smem = sizeof(float) * 8 * (size_t)g.DP;
-    const int grid = std::min(a.nb, irec_device().sm_count * 2);
+    // 3 CTAs of 8 warps per SM (launch bounds): the per-sample Philox -> Box-Muller -> fma chain is latency-bound
+    const int grid = std::min(a.nb, irec_device().sm_count * (smem * 3 <= (size_t)200 * 1024 ? 3 : 2));
     if (encode) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_is_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
