@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--min-aux", type=int, default=8)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare with the CPU oracle where S is small enough")
+    ap.add_argument("--graph", action="store_true", help="replay the per-variable step loop from a CUDA graph")
     args = ap.parse_args()
 
     import torch
@@ -60,6 +61,9 @@ def main():
         d = [torch.as_tensor(a, device=dev).contiguous() for a in (mu, sig, pl, ps)]
         blk = engine.ShardedBeamBlock(D, S, B, omega, max_aux=256, device=dev)
         idx, sample = blk.encode(*d, seed=42)            # warm-up + result
+        if args.graph:
+            idx_g, sample_g = blk.encode_graphed(*d, seed=42)        # captures; must reproduce the eager result
+            assert idx_g == idx and torch.equal(sample_g, sample), "graphed encode differs from the eager one"
         times = []
         for _ in range(args.reps):
             torch.cuda.synchronize()
@@ -68,8 +72,11 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             n_aux = blk.init(*d, seed=42)
-            for t in range(n_aux):
-                blk.step(t)
+            if args.graph:
+                blk._graphs[n_aux].replay()
+            else:
+                for t in range(n_aux):
+                    blk.step(t)
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -80,7 +87,8 @@ def main():
         n_aux = len(idx)
         cand = S + (n_aux - 1) * S * min(B, S)
         line = {"workload": "C5 sweep: one coder-block, candidate range sharded", "omega_bits": bits, "S": S, "D": D, "n_beams": B,
-                "n_aux": n_aux, "n_gpus": world, "ms": ms, "candidates_per_sec": cand / (ms * 1e-3),
+                "n_aux": n_aux, "n_gpus": world, "cuda_graph": bool(args.graph),
+                "exchange": ("peer-memory stores (irec_p2p_exchange)" if blk.p2p is not None else ("nccl all_gather" if world > 1 else "none")), "ms": ms, "candidates_per_sec": cand / (ms * 1e-3),
                 "candidate_dims_per_sec": cand * D / (ms * 1e-3), "partitions_per_sec": n_aux / (ms * 1e-3)}
         if args.check and S * B * D <= 4e8:
             from oracle import oracle as O
@@ -90,6 +98,10 @@ def main():
         if rank == 0:
             print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        blk._graphs.clear()
+        del blk
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -154,6 +154,17 @@ int irec_beam_state_finish(void* state, int D, const int64_t* gather_idx, int64_
 int irec_topb_merge(const irec_record_t* records, int n_records, int Bcur, int B, irec_record_t* out_records,
                     int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Exchange step of the candidate-range sharded coder over NVLink peer memory instead of an NCCL all-gather
+ * (the argsort at beam_search_coder.py:86 split across GPUs).  peer_bufs: DEVICE array of `world`
+ * pointers to the ranks' exchange buffers (symmetric allocations of irec_p2p_exchange_bytes(B, world) bytes,
+ * zero-initialised, peer-mapped into this process, entry `rank` = the local one).  Pushes the B records + count of
+ * this rank (layout of irec_beam_step_score's out_records / out_count, contiguous) to every rank, waits for every
+ * rank's records of the same step, writes them as out_records [world][B] / out_counts [world] for
+ * irec_beam_step_commit.  Every rank must call it the same number of times. */
+size_t irec_p2p_exchange_bytes(int B, int world);
+int irec_p2p_exchange(void* const* peer_bufs, int rank, int world, int B, const irec_record_t* local_records_and_count,
+                      irec_record_t* out_records, int32_t* out_counts, void* stream);
+
 /* ---- importance sampler (rec/coding/importance_sampling.py, samplers.py:61-101) -------------- */
 
 /* encode_gaussian_importance_sample with alpha = inf (importance_sampling.py:9-79): one partition,

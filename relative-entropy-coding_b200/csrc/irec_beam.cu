@@ -1061,6 +1061,71 @@ int irec_topb_merge(const irec_record_t* records, int n_records, int Bcur, int B
     return irec_check_launch("k_topb_merge");
 }
 
+// ---------------- record exchange over NVLink peer memory --------------------------------------------
+// The candidate-range sharded coder exchanges (B + 1) 16-byte records per rank and auxiliary variable: 336 bytes.  At
+// that size an NCCL all-gather is pure latency (launch + protocol, ~20-40 us on 8 GPUs) and sits between two small
+// kernels.  Here every rank STORES its records straight into every peer's exchange buffer (peer-mapped device memory,
+// NVLink / NVSwitch) and raises a per-sender sequence flag with a system-scope release; it then spins on its own flags
+// (system-scope acquire) until all peers' records of this step have landed, and hands them to the merge.
+// Exchange buffer of one rank (int32 words; allocated symmetric on all ranks, zero-initialised):
+//   [0]               steps completed by the owner (device-side sequence counter: CUDA-graph replays stay in step)
+//   [64 .. 64+world)  flag[sender] = last sequence number `sender` has pushed here
+//   [128 ..)          slot[parity][sender][(B + 1) * 4]   (parity = sequence & 1: a fast sender's next step never lands
+//                     in the slot its peers are still reading)
+#define P2P_FLAG_OFF 64
+#define P2P_SLOT_OFF 128
+__global__ void __launch_bounds__(256) k_p2p_exchange(int32_t* const* __restrict__ peer_bufs, int rank, int world, int B,
+                                                       const int32_t* __restrict__ local, int32_t* __restrict__ out_records,
+                                                       int32_t* __restrict__ out_counts)
+{
+    __shared__ int s_seq;
+    int32_t* mine = peer_bufs[rank];
+    if (threadIdx.x == 0) s_seq = mine[0] + 1;
+    __syncthreads();
+    const int seq = s_seq, W = (B + 1) * 4, parity = seq & 1;
+    // push: my records into slot[parity][rank] of every rank (my own included)
+    for (int i = threadIdx.x; i < world * W; i += blockDim.x) {
+        const int r = i / W, w = i - r * W;
+        peer_bufs[r][P2P_SLOT_OFF + (parity * world + rank) * W + w] = local[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        int32_t* flag = peer_bufs[threadIdx.x] + P2P_FLAG_OFF + rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+        // wait: the records of every sender for this step
+        const int32_t* want = mine + P2P_FLAG_OFF + threadIdx.x;
+        int got;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(got) : "l"(want) : "memory");
+        } while (got - seq < 0);
+    }
+    __syncthreads();
+    const volatile int32_t* slots = mine + P2P_SLOT_OFF + parity * world * W;
+    for (int i = threadIdx.x; i < world * B * 4; i += blockDim.x) {
+        const int r = i / (B * 4), w = i - r * (B * 4);
+        out_records[i] = slots[r * W + w];
+    }
+    for (int r = threadIdx.x; r < world; r += blockDim.x) out_counts[r] = slots[r * W + B * 4];
+    __syncthreads();
+    if (threadIdx.x == 0) mine[0] = seq;
+}
+
+size_t irec_p2p_exchange_bytes(int B, int world) { return sizeof(int32_t) * (P2P_SLOT_OFF + 2 * (size_t)world * (size_t)(B + 1) * 4); }
+
+int irec_p2p_exchange(void* const* peer_bufs, int rank, int world, int B, const irec_record_t* local_records_and_count,
+                      irec_record_t* out_records, int32_t* out_counts, void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || B <= 0 || B > 32)
+        return irec_fail(IREC_E_INVALID, "p2p_exchange: bad rank / world / B");
+    k_p2p_exchange<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<int32_t* const*>(peer_bufs), rank, world, B,
+                                                        reinterpret_cast<const int32_t*>(local_records_and_count),
+                                                        reinterpret_cast<int32_t*>(out_records), out_counts);
+    irec_count_launch();
+    return irec_check_launch("k_p2p_exchange");
+}
+
 // ---------------- the block-batched entry point ------------------------------------------------
 size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, int B, int max_aux)
 {

@@ -6,6 +6,8 @@ CUDA tensor [nb+1]).  Results needed on the host (index lists) cost exactly one 
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import native as N
@@ -241,6 +243,32 @@ class ShardedBeamBlock:
         # one gather buffer: per rank B records (16 B each) followed by the count in the last record slot
         self.local, self.gathered = SH.alloc_exchange(self.B, self.world, self.device)
         self.s_begin, self.s_end = SH.candidate_range(self.S, self.rank, self.world)
+        self._graphs = {}
+        self.p2p = None
+        if self.world > 1 and os.environ.get("IREC_P2P", "1") != "0":
+            self.p2p = self._setup_p2p()
+
+    def _setup_p2p(self):
+        """symmetric exchange buffers mapped into every rank (torch symmetric memory: NVLink peer access); None if the
+        platform cannot provide them (then the records go through an NCCL all-gather)"""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else self.dist.group.WORLD
+            words = int(N.lib().irec_p2p_exchange_bytes(self.B, self.world)) // 4
+            buf = symm.empty(words, dtype=torch.int32, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, grp)
+            ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+            out_rec = torch.zeros(self.world * self.B * SH.RECORD_WORDS, dtype=torch.int32, device=self.device)
+            out_cnt = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+            self.dist.barrier(group=self.group)
+            return {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rec": out_rec, "cnt": out_cnt}
+        except Exception as e:              # noqa: BLE001  (no peer access / symmetric memory unavailable)
+            if os.environ.get("IREC_P2P") == "1":
+                raise
+            self.p2p_error = repr(e)
+            return None
 
     def init(self, t_loc, t_scale, p_loc, p_scale, seed):
         lib = N.lib()
@@ -263,9 +291,36 @@ class ShardedBeamBlock:
         cnt_ptr = C.c_void_p(self.local.data_ptr() + B * N.RECORD_BYTES)
         N.check(lib.irec_beam_step_score(N.ptr(self.state), self.D, B, t, self.s_begin, self.s_end, 1, rec_ptr, cnt_ptr,
                                          N.ptr(self.ws), self.ws_bytes, N.stream_ptr()), "irec_beam_step_score")
-        recs, counts = SH.exchange_records(self.local, self.gathered, B, self.world, self.dist, self.group)
+        if self.p2p is not None:
+            recs, counts = self.p2p["rec"], self.p2p["cnt"]
+            N.check(lib.irec_p2p_exchange(N.ptr(self.p2p["ptrs"]), self.rank, self.world, B, rec_ptr, N.ptr(recs),
+                                          N.ptr(counts), N.stream_ptr()), "irec_p2p_exchange")
+        else:
+            recs, counts = SH.exchange_records(self.local, self.gathered, B, self.world, self.dist, self.group)
         N.check(lib.irec_beam_step_commit(N.ptr(self.state), self.D, B, t, N.ptr(recs), N.ptr(counts), self.world,
                                           N.ptr(self.ws), self.ws_bytes, N.stream_ptr()), "irec_beam_step_commit")
+
+    def capture_steps(self, n_aux):
+        """CUDA graph of the n_aux (score -> all-gather -> merge + commit) steps: ~10 small launches and one NCCL
+        collective per auxiliary variable are launch-bound below S ~ 2^22, so they are captured once and replayed.
+        Call after init() (the graph reads and advances the block state in place); every rank must capture."""
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(graph, stream=side):
+            for t in range(n_aux):
+                self.step(t)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return graph
+
+    def encode_graphed(self, t_loc, t_scale, p_loc, p_scale, seed, graphs=None):
+        """encode() with the step loop replayed from a CUDA graph (cached per n_aux in `graphs`)"""
+        n_aux = self.init(t_loc, t_scale, p_loc, p_scale, seed)
+        graphs = self._graphs if graphs is None else graphs
+        if n_aux not in graphs:
+            graphs[n_aux] = self.capture_steps(n_aux)
+        graphs[n_aux].replay()
+        return self.finish()
 
     def finish(self):
         lib = N.lib()
