@@ -397,3 +397,27 @@ def test_sharded_block_nccl_two_ranks(cuda):
                         "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "run_sharded_nccl.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sharded nccl ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_p2p_exchange_single_rank_loopback(cuda):
+    """k_p2p_exchange with world = 1 (the rank's own buffer is its only peer): records come back unchanged, the device-side
+    step counter advances, both parity slots get used.  The multi-rank path is exercised by bench_sweep.py --check under
+    torchrun (profiles/r1_sweep_c5_*_p2p_graph.jsonl: matches_oracle)."""
+    import ctypes as C
+    import torch
+    from irec_b200 import native as N
+    lib = N.lib()
+    B = 20
+    words = int(lib.irec_p2p_exchange_bytes(B, 1)) // 4
+    buf = torch.zeros(words, dtype=torch.int32, device=cuda)
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=cuda)
+    out_rec = torch.zeros(B * 4, dtype=torch.int32, device=cuda)
+    out_cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    for step in range(1, 4):
+        local = torch.arange((B + 1) * 4, dtype=torch.int32, device=cuda) * step
+        local[B * 4] = 7 + step
+        N.check(lib.irec_p2p_exchange(N.ptr(ptrs), 0, 1, B, N.ptr(local), N.ptr(out_rec), N.ptr(out_cnt), N.stream_ptr()),
+                "irec_p2p_exchange")
+        torch.cuda.synchronize()
+        assert torch.equal(out_rec, local[:B * 4]) and int(out_cnt[0]) == 7 + step
+        assert int(buf[0]) == step and int(buf[64]) == step

@@ -1,0 +1,77 @@
+"""Code-generation canary for the hot loop of k_beam_encode_resident2<20> (no GPU needed: reads the SASS of the built
+libirec.so).  ptxas sits close to the 168-register cap of a 384-thread CTA there, and twice during development an
+unrelated edit elsewhere in the kernel made it serialise the quantile gathers (LDS followed directly by its use:
+39.0 ms per launch instead of 35.7 ms).  This test fails if that happens again:
+the median distance (in instructions) between a table gather and the first use of its result must stay >= 10, and the
+loop body must not touch local memory more than a couple of times."""
+import os
+import re
+import shutil
+import statistics
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "relative-entropy-coding_b200", "lib", "libirec.so")
+
+
+def _kernel_sass(tmp):
+    subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True, check=True)
+    cub = [f for f in os.listdir(tmp) if f.startswith("irec_beam.")][0]
+    dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True, check=True).stdout
+    out, on, cur = [], False, None
+    for ln in dis.splitlines():
+        if ln.startswith(".text."):
+            on = "k_beam_encode_resident2ILi20E" in ln
+            continue
+        if not on:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = int(m.group(2)) if m.group(1).endswith("irec_resident2.cuh") else -1
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)
+        if m:
+            out.append((cur, m.group(1).strip()))
+    return out
+
+
+def test_quantile_gathers_stay_software_pipelined(built):
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")):
+        pytest.skip("CUDA binary utilities not available")
+    src = open(os.path.join(ROOT, "relative-entropy-coding_b200", "csrc", "irec_resident2.cuh")).read().splitlines()
+    gather_line = 1 + next(i for i, l in enumerate(src) if "tv[g][e] = *reinterpret_cast<const float*>(T2b + (ad[k][e] + cb[g]));" in l)
+    with tempfile.TemporaryDirectory() as tmp:
+        ins = _kernel_sass(tmp)
+    # the unrolled loop body = the longest run of instructions attributed to the scoring chunk (source lines of r2_score_chunk)
+    lo, hi = gather_line - 50, gather_line + 20
+    best, i = (0, 0, 0), 0
+    while i < len(ins):
+        if lo <= ins[i][0] <= hi:
+            j = i
+            while j < len(ins) and (lo <= ins[j][0] <= hi or ins[j][0] in range(28, 42)):
+                j += 1
+            if j - i > best[0]:
+                best = (j - i, i, j)
+            i = j
+        else:
+            i += 1
+    body = ins[best[1]:best[2]]
+    assert len(body) > 400, "hot loop not found in the SASS"
+    dist = []
+    for k, (line, text) in enumerate(body):
+        m = re.match(r"LDS R(\d+), ", text)
+        if not (m and line == gather_line):
+            continue
+        reg = re.compile(r"\bR" + m.group(1) + r"\b")
+        for n in range(k + 1, len(body)):
+            ops = body[n][1].split(",", 1)
+            if len(ops) > 1 and reg.search(ops[1]):
+                dist.append(n - k)
+                break
+    assert len(dist) >= 60, len(dist)
+    local = sum(1 for _, t in body if re.match(r"(LDL|STL)", t))
+    assert statistics.median(dist) >= 10, (statistics.median(dist), sorted(dist)[:10])
+    assert local <= 4, local
