@@ -27,7 +27,12 @@ __device__ __forceinline__ float is_score_chunk(const float4* __restrict__ A4, c
 {
     float acc = 0.f;
     const bool aligned = (j_base & 3) == 0;
-#pragma unroll 1
+#ifndef IREC_IS_UNROLL
+#define IREC_IS_UNROLL 1
+#endif
+#define IREC_PRAGMA_(x) _Pragma(#x)
+#define IREC_UNROLL_(n) IREC_PRAGMA_(unroll n)
+    IREC_UNROLL_(IREC_IS_UNROLL)
     for (int iq = 0; iq < 8; ++iq) {
         float4 z;
         if (aligned) {
