@@ -70,8 +70,30 @@ class BeamEncodeResult:
         self.indices, self.n_aux, self.sample, self.kl = indices, n_aux, sample, kl
 
 
+class PendingBeamResult:
+    """Result of a launched beam encode whose index lists have not been read back yet: the packed (status, n_aux, indices)
+    rows are on their way to pinned host memory; `indices()` waits for that copy only (not for later work on the stream),
+    checks the per-block status and builds the Python lists.  Lets a caller that codes several tensors in a row (the
+    levels of a model, a batch of images) overlap the host-side list building of one launch with the next launch."""
+    __slots__ = ("_host", "_event", "_nb", "sample", "kl", "_lists")
+
+    def __init__(self, host, event, nb, sample, kl):
+        self._host, self._event, self._nb, self.sample, self.kl, self._lists = host, event, nb, sample, kl, None
+
+    def indices(self):
+        if self._lists is None:
+            self._event.synchronize()
+            packed = self._host
+            status, n_aux, idx = packed[:, 0], packed[:, 1], packed[:, 2:]
+            _raise_status(status, n_aux, "beam encode")
+            idx_np, na_np = idx.numpy(), n_aux.numpy().tolist()
+            self._lists = [idx_np[b, :na_np[b]].tolist() for b in range(self._nb)]
+            self._host = None
+        return self._lists
+
+
 def beam_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, max_block_dim, omega, S, B, seed,
-                       max_aux=None, return_device=False):
+                       max_aux=None, return_device=False, lazy=False):
     """BeamSearchCoder.encode_block over nb blocks in one launch (beam_search_coder.py:53-122)."""
     lib = N.lib()
     dev = t_loc.device
@@ -95,6 +117,13 @@ def beam_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets
                                  N.ptr(ws), ws_bytes, N.stream_ptr()), "irec_beam_encode")
     if return_device:
         return BeamEncodeResult(out_idx, out_na, out_sample, kl), out_st
+    if lazy:
+        packed_dev = torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1)
+        host = torch.empty(packed_dev.shape, dtype=packed_dev.dtype, pin_memory=True)
+        host.copy_(packed_dev, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        return PendingBeamResult(host, event, nb, out_sample, kl)
     packed = torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1).cpu()   # one D2H copy
     status, n_aux, idx = packed[:, 0], packed[:, 1], packed[:, 2:]
     _raise_status(status, n_aux, "beam encode")

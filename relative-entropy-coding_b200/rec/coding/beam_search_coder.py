@@ -69,9 +69,12 @@ class BeamSearchCoder(GaussianCoder):
         return len(indicies) * np.log(self.n_samples)               # reference :150-151
 
     # -- extension: a batch of independent tensors (e.g. images) in one launch ----------------------
-    def encode_batch(self, target_dist, coding_dist, seed):
+    def encode_batch(self, target_dist, coding_dist, seed, lazy=False):
         """Codes every row of a [N, ...] batch independently with the same coding seed -- what looping the
-        reference's `encode` over N single-image batches computes.  Returns (indices[N][n_blocks][n_aux], sample)."""
+        reference's `encode` over N single-image batches computes.  Returns (indices[N][n_blocks][n_aux], sample).
+        With lazy=True the first element is a callable: the kernel has been launched and the sample tensor is valid in
+        stream order, the index lists are read back and built when it is called (so that the caller can launch the
+        next tensor first)."""
         self._check_ratios()
         tl, ts = _dist_tensors(target_dist)
         pl, ps = _dist_tensors(coding_dist)
@@ -83,14 +86,22 @@ class BeamSearchCoder(GaussianCoder):
             perm = self._permutation(n, seed, tl.device)
             gather = (perm[None, :] + torch.arange(n_items, device=tl.device)[:, None] * n).reshape(-1).contiguous()
         offsets, nb, max_dim = E.make_block_offsets(n, self.block_size, tl.device, n_items=n_items)
+        per = nb // n_items
+        block_size = self.block_size
+
+        def nest(indices):
+            if block_size is None:
+                return [indices[i] for i in range(n_items)]
+            return [indices[i * per:(i + 1) * per] for i in range(n_items)]
+
+        if lazy:
+            with self._ratios_ctx(tl.device):
+                pend = E.beam_encode_blocks(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), gather, offsets,
+                                            nb, max_dim, self.kl_per_partition, self.n_samples, self.n_beams, seed, lazy=True)
+            return (lambda: nest(pend.indices())), pend.sample.reshape(shape)
         indices, sample = self._encode_flat(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), gather,
                                             offsets, nb, max_dim, seed)
-        per = nb // n_items
-        if self.block_size is None:
-            nested = [indices[i] for i in range(n_items)]
-        else:
-            nested = [indices[i * per:(i + 1) * per] for i in range(n_items)]
-        return nested, sample.reshape(shape)
+        return nest(indices), sample.reshape(shape)
 
     def decode_batch(self, coding_dist, indices, seed):
         self._check_ratios()

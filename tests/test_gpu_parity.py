@@ -421,3 +421,21 @@ def test_p2p_exchange_single_rank_loopback(cuda):
         torch.cuda.synchronize()
         assert torch.equal(out_rec, local[:B * 4]) and int(out_cnt[0]) == 7 + step
         assert int(buf[0]) == step and int(buf[64]) == step
+
+
+def test_encode_batch_lazy_equals_eager(cuda):
+    """encode_batch(lazy=True): index lists read back on demand == the synchronous call, launches may be interleaved"""
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=500)
+    arrs = [synth.c2(1200, data_seed=300 + i) for i in range(3)]
+    t = Normal(np.stack([a[0] for a in arrs]), np.stack([a[1] for a in arrs]), device=cuda)
+    p = Normal(np.stack([a[2] for a in arrs]), np.stack([a[3] for a in arrs]), device=cuda)
+    eager_idx, eager_sample = coder.encode_batch(t, p, seed=42)
+    get1, s1 = coder.encode_batch(t, p, seed=42, lazy=True)
+    get2, s2 = coder.encode_batch(t, p, seed=43, lazy=True)          # a second launch before the first is read back
+    assert get1() == eager_idx and torch.equal(s1, eager_sample)
+    other_idx, other_sample = coder.encode_batch(t, p, seed=43)
+    assert get2() == other_idx and torch.equal(s2, other_sample)
+    assert get1() is get1() or get1() == eager_idx                     # cached
