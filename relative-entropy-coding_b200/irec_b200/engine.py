@@ -5,7 +5,6 @@ All functions take float32 CUDA tensors (flattened) plus the block structure of 
 CUDA tensor [nb+1]).  Results needed on the host (index lists) cost exactly one device->host copy.
 """
 import ctypes as C
-
 import os
 
 import torch
