@@ -13,6 +13,7 @@
 #include "irec_beam.cuh"
 #include "irec_host.h"
 #include <string.h>
+#include <mutex>
 
 // =============================================================================================
 // k_kl_naux
@@ -759,6 +760,78 @@ static size_t r2_ws_sched_bytes()
 {
     return sizeof(float) * 4 * 1024 * (size_t)irec_device().sm_count;      // [grid][4][DPmax <= 1024]
 }
+// ---- library-owned exponent table, reused across launches (R2TabKey) ----
+#define R2_CACHE_MAX_BYTES ((size_t)256 << 20)
+struct R2TabCache {
+    std::mutex mu;
+    void* buf = nullptr; size_t bytes = 0;
+    R2TabKey* key = nullptr;                       // device
+    int64_t seed = 0; int S = 0, row_stride = 0, cap_aux = 0;
+    bool have_params = false;
+    cudaEvent_t ev = nullptr; cudaStream_t last = nullptr; bool ev_valid = false;
+};
+static R2TabCache g_tab_cache[64];
+
+struct R2TabUse { uint2* tab; int tab_aux; R2TabKey* key; R2TabCache* cache; };
+
+// table for this launch: the per-device cache when it can be used (capacity, not capturing, IREC_R2_NO_CACHE unset),
+// otherwise `ws_tab` inside the caller's workspace.  On success with a cache the mutex is HELD until r2_tab_release.
+static R2TabUse r2_tab_acquire(uint2* ws_tab, int64_t seed, int S, int max_aux, int row_stride, cudaStream_t s)
+{
+    R2TabUse u{ ws_tab, max_aux, nullptr, nullptr };
+    const char* e = getenv("IREC_R2_NO_CACHE");
+    if (e && e[0] == '1') return u;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return u;
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return u;
+    R2TabCache& c = g_tab_cache[d];
+    const int cap_aux = std::max(128, (max_aux + 63) / 64 * 64);
+    const size_t need = sizeof(uint2) * (size_t)R2_MAX_SIZES * (size_t)cap_aux * (size_t)S * (size_t)row_stride;
+    if (need > R2_CACHE_MAX_BYTES) return u;
+    c.mu.lock();
+    bool fresh = false;
+    if (!c.key) {
+        if (cudaMalloc(&c.key, sizeof(R2TabKey)) != cudaSuccess || cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError(); c.key = nullptr; c.mu.unlock(); return u;
+        }
+        fresh = true;
+    }
+    if (need > c.bytes) {
+        if (c.buf) { cudaDeviceSynchronize(); cudaFree(c.buf); c.buf = nullptr; c.bytes = 0; }
+        if (cudaMalloc(&c.buf, need) != cudaSuccess) { cudaGetLastError(); c.mu.unlock(); return u; }
+        c.bytes = need;
+        fresh = true;
+    }
+    if (c.ev_valid && c.last != s) cudaStreamWaitEvent(s, c.ev, 0);          // another stream may still be using the table
+    const bool same = c.have_params && c.seed == seed && c.S == S && c.row_stride == row_stride && c.cap_aux >= cap_aux;
+    if (fresh || !same) {
+        cudaMemsetAsync(c.key, 0, sizeof(R2TabKey), s);
+        c.seed = seed; c.S = S; c.row_stride = row_stride; c.cap_aux = cap_aux; c.have_params = true;
+    }
+    u.tab = reinterpret_cast<uint2*>(c.buf); u.tab_aux = c.cap_aux; u.key = c.key; u.cache = &c;
+    return u;
+}
+static void r2_tab_release(const R2TabUse& u, cudaStream_t s)
+{
+    if (!u.cache) return;
+    cudaEventRecord(u.cache->ev, s);
+    u.cache->ev_valid = true; u.cache->last = s;
+    u.cache->mu.unlock();
+}
+// exponent rows of this launch (skipping what the cache already holds) + the cache bookkeeping kernel
+static void r2_build_table(const R2TabUse& u, const R2Plan* dplan, int64_t seed, int S, int max_aux, int row_stride, cudaStream_t s)
+{
+    const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;          // one thread per gather family
+    const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
+    k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, u.tab_aux, row_stride, u.tab, u.key);
+    irec_count_launch();
+    if (u.key) {
+        k_r2_key_commit<<<1, 1, 0, s>>>(dplan, u.key, max_aux);
+        irec_count_launch();
+    }
+}
+
 static size_t r2_table_bytes(int max_D, int S, int max_aux)
 {
     if (max_D > 1024) return 0;
@@ -1185,15 +1258,18 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
         const uint2* tab = nullptr;
         if (tab_bytes && !r2_no_table()) {
             uint2* t = reinterpret_cast<uint2*>(w + 512 + irec_cluster_hist_bytes(nb, max_aux) + r2_ws_order_bytes(nb));
-            const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;
-            const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
-            k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, make_geom((int)max_block_dim).DP >> 2, t);
-            irec_count_launch();
-            tab = t;
+            const int row_stride = make_geom((int)max_block_dim).DP >> 2;
+            const R2TabUse u = r2_tab_acquire(t, seed, S, max_aux, row_stride, s);
+            r2_build_table(u, dplan, seed, S, max_aux, row_stride, s);
+            const int rc = irec_launch_cluster(cluster_G, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim,
+                                               omega, S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
+                                               dplan, u.tab, u.tab_aux, s);
+            r2_tab_release(u, s);
+            return rc;
         }
         return irec_launch_cluster(cluster_G, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim, omega,
                                    S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
-                                   tab ? dplan : nullptr, tab, s);
+                                   nullptr, tab, max_aux, s);
     }
     if (!irec_force_general() && rchoice != 1) {
         const ResidentPlan plan2 = plan_resident2(nb, (int)max_block_dim, S, B);
@@ -1210,7 +1286,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             a.hist = reinterpret_cast<int2*>(w + 512);
             a.sched = reinterpret_cast<float*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux));
             a.work_counter = counter; a.DPmax = plan2.DPmax; a.NC = plan2.NC;
-            a.plan = nullptr; a.tab = nullptr;
+            a.plan = nullptr; a.tab = nullptr; a.tab_aux = max_aux;
             // distinct block sizes + the queue order (largest blocks first)
             R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
             int32_t* order = reinterpret_cast<int32_t*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes());
@@ -1222,11 +1298,12 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             if (tab_bytes && !r2_no_table()) {
                 // exponent table of this launch (the candidate stream is the same for every coder-block)
                 uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb));
-                const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;      // one thread per gather family
-                const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
-                k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, plan2.DPmax >> 2, tab);
-                irec_count_launch();
-                a.plan = dplan; a.tab = tab;
+                const R2TabUse u = r2_tab_acquire(tab, seed, S, max_aux, plan2.DPmax >> 2, s);
+                r2_build_table(u, dplan, seed, S, max_aux, plan2.DPmax >> 2, s);
+                a.plan = dplan; a.tab = u.tab; a.tab_aux = u.tab_aux;
+                launch_resident2(plan2, a, s);
+                r2_tab_release(u, s);
+                return irec_check_launch("k_beam_encode_resident2");
             }
             launch_resident2(plan2, a, s);
             return irec_check_launch("k_beam_encode_resident2");

@@ -281,6 +281,15 @@ struct R2Plan {
     int32_t D[R2_MAX_SIZES];
     int32_t pad;
 };
+// Device-side description of what a (library-owned, reused) exponent table currently holds.  The table depends on
+// (seed, S, row stride, the block sizes, t) only -- a model codes all of its latent tensors with the same seed
+// (resnet_vae.py:824), so after the first launch the later ones find their rows already there.  The host invalidates
+// it when seed / S / stride / capacity change; the block sizes are known on the device only and are checked there.
+struct R2TabKey {
+    int32_t valid;
+    int32_t D[R2_MAX_SIZES];
+    int32_t filled;                // rows t < filled are present for both sizes
+};
 
 #ifndef IREC_R2_DEVICE_ONLY      // the __global__ kernels below belong to irec_beam.cu only
 // Also writes `order`: the coder-blocks sorted by decreasing size (counting sort), the sequence in which the
@@ -307,6 +316,10 @@ __global__ void __launch_bounds__(1024) k_r2_plan(const int64_t* __restrict__ of
         int n = 0;
         for (int k = 0; k < R2_MAX_SIZES; ++k) n += plan->D[k] != 0;
         plan->n_sizes = n;
+        for (int i = 1; i < R2_MAX_SIZES; ++i)             // canonical (descending) order: the CAS race above must not
+            for (int j = i; j > 0 && plan->D[j] > plan->D[j - 1]; --j) {      // decide which table slot a size gets
+                const int tmp = plan->D[j]; plan->D[j] = plan->D[j - 1]; plan->D[j - 1] = tmp;
+            }
         int run = 0;
         for (int i = 0; i < 1025; ++i) { const int c = s_cnt[i]; s_cnt[i] = run; run += c; }   // exclusive prefix
     }
@@ -324,9 +337,30 @@ __global__ void __launch_bounds__(1024) k_r2_plan(const int64_t* __restrict__ of
 // serves more than `cap` lanes: greedy "less loaded of the two banks", one-hop relocation when both are full,
 // cap raised from 2 only if that fails.  Any assignment yields the same values (T2[a] == T2[a + 10006]).
 #define R2_BANK_SHIFT (IREC_ORD & 31u)
-__global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
-                                                 int64_t seed, int S, int max_aux, int row_stride, uint2* __restrict__ tab)
+__global__ void k_r2_key_commit(const R2Plan* __restrict__ plan, R2TabKey* key, int max_aux)
 {
+    bool same = key->valid != 0;
+    for (int k = 0; k < R2_MAX_SIZES; ++k) same = same && key->D[k] == plan->D[k];
+    const int have = same ? key->filled : 0;
+    for (int k = 0; k < R2_MAX_SIZES; ++k) key->D[k] = plan->D[k];
+    key->filled = have > max_aux ? have : max_aux;
+    key->valid = 1;
+}
+
+// tab_aux: rows per size the table is laid out for (>= max_aux); key: nullptr, or the cache key -- rows it already
+// covers for these block sizes are skipped (k_r2_key_commit, launched right after, records the new state)
+__global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
+                                                 int64_t seed, int S, int max_aux, int tab_aux, int row_stride,
+                                                 uint2* __restrict__ tab, const R2TabKey* __restrict__ key)
+{
+    int t_first = 0;
+    if (key) {
+        bool same = key->valid != 0;
+#pragma unroll
+        for (int k = 0; k < R2_MAX_SIZES; ++k) same = same && key->D[k] == plan->D[k];
+        t_first = same ? key->filled : 0;
+        if (t_first >= max_aux) return;
+    }
     const int64_t per_size = (int64_t)max_aux * S * 8;
     const int64_t total = per_size * R2_MAX_SIZES;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -337,6 +371,7 @@ __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan
         const int iqd = (int)(r & 7); r >>= 3;
         const int sg = (int)(r % S);
         const int t = (int)(r / S);
+        if (t < t_first) continue;
         const BeamGeom g = make_geom(D);
         if (sg * g.SPW >= S) continue;
         const TfStream st = tf_stream_seeded(seed + t, seed + t);
@@ -395,7 +430,7 @@ __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan
             }
             pick[q] = ch;
         }
-        uint2* out = tab + (size_t)k * max_aux * S * row_stride + (size_t)t * S * row_stride;
+        uint2* out = tab + (size_t)k * tab_aux * S * row_stride + (size_t)t * S * row_stride;
         for (int lane = 0; lane < 32; ++lane) {
             const int row = lane / g.P, l = lane & (g.P - 1);
             const int s = sg * g.SPW + row;
@@ -564,7 +599,8 @@ struct Resident2Args {
     float* sched;          // [gridDim.x][4][DPmax] per-CTA scratch: sigma_p^2, sigma_t^2, delta mu, cumulative variance
     const int32_t* order;  // queue position -> coder-block (largest blocks first), or nullptr
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
-    const uint2* tab;      // [R2_MAX_SIZES][max_aux][S][DPmax / 4]
+    const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
+    int tab_aux;           // rows per size in the table layout (>= max_aux)
 };
 
 template <int BMAX>
@@ -621,7 +657,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         if (a.tab) {
 #pragma unroll
             for (int k = 0; k < R2_MAX_SIZES; ++k)
-                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.max_aux * a.S * row_stride;
+                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
         }
 
         // ---- load + KL (coder.py:499-501) ----

@@ -439,3 +439,39 @@ def test_encode_batch_lazy_equals_eager(cuda):
     other_idx, other_sample = coder.encode_batch(t, p, seed=43)
     assert get2() == other_idx and torch.equal(s2, other_sample)
     assert get1() is get1() or get1() == eager_idx                     # cached
+
+
+def test_exponent_table_cache_is_transparent(cuda):
+    """The per-device cache of the exponent table (rows kept across launches for equal seed / S / block sizes) must never
+    change a result: a sequence of launches that hits, extends (more auxiliary variables), misses (other block sizes) and
+    invalidates (other seed) the cache gives the same indices and sample bits as with IREC_R2_NO_CACHE=1."""
+    import os
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+
+    def tensor(n, seed, boost=1.0):
+        tl, ts, pl, ps = synth.c2(n, data_seed=seed)
+        tl = (pl + boost * (tl - pl)).astype(np.float32)
+        return Normal(tl[None], ts[None], device=cuda), Normal(pl[None], ps[None], device=cuda)
+
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=1000)
+    calls = [(tensor(3192, 1), 42), (tensor(3192, 2), 42), (tensor(3192, 3, boost=1.6), 42),     # hit, then more variables
+             (tensor(2500, 4), 42), (tensor(3192, 1), 42),                                          # other sizes, back again
+             (tensor(3192, 1), 43), (tensor(3192, 5), 42)]                                          # other seed, back again
+    def run():
+        out = []
+        for (t, p), seed in calls:
+            idx, sample = coder.encode(t, p, seed=seed)
+            out.append((idx, sample.clone()))
+        return out
+    os.environ["IREC_R2_NO_CACHE"] = "1"
+    try:
+        ref = run()
+    finally:
+        del os.environ["IREC_R2_NO_CACHE"]
+    got = run()
+    again = run()
+    for (ri, rs), (gi, gs), (ai, as_) in zip(ref, got, again):
+        assert gi == ri and torch.equal(gs, rs)
+        assert ai == ri and torch.equal(as_, rs)
