@@ -529,6 +529,129 @@ __global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
     if (tid == 0) a.out_cnt[blockIdx.x] = Kout;
 }
 
+// ---- second generation of the general-path scoring kernel (D <= 1024): discrete-log addressing with the exponent
+// computed in place (S is far too large for a table here: 2^24 samples x 64 dims), in-place two-choice bank assignment
+// (r2_spread_banks), beams in passes of R2Pass::HB.  First generation (profiles/r1_gp_score_ncu.md): 255 registers,
+// three IMADs per candidate-dim, 3.5 shared-memory wavefronts per gather, data pipe 74 % busy.  Same scores bit for bit.
+#define GP2_THREADS 512
+struct Score2Args {
+    void* state; int t; const float* T2; const uint16_t* dl4;
+    int64_t s_begin, s_end;
+    irec_record_t* out_rec; int32_t* out_cnt;
+    int cand_cap;
+};
+struct Gp2Sink {
+    float* s_csc; int32_t* s_cid; int32_t* s_cnt;
+    float tau; int Bcur, boff; int s_end; bool warp_valid;
+    __device__ __forceinline__ void operator()(int sk, int b, float x, bool dup) const
+    {
+        b += boff;
+        if (dup || !warp_valid || b >= Bcur || sk >= s_end) return;
+        const float v = (x == x) ? x : __int_as_float(0xff800000);
+        if (v >= tau) {
+            const int pos = atomicAdd(s_cnt, 1);
+            s_csc[pos] = v;
+            s_cid[pos] = sk * Bcur + b;
+        }
+    }
+};
+
+template <int BMAX>
+__global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_score_topb2(const Score2Args a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(a.state);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (hdr->status != IREC_BLK_OK || a.t >= hdr->n_aux) {
+        if (tid == 0) a.out_cnt[blockIdx.x] = 0;
+        return;
+    }
+    BeamGeom g;
+    g.D = hdr->D; g.P = hdr->P; g.nslots = hdr->nslots; g.DP = hdr->DP; g.nch = (g.D + 31) >> 5; g.SPW = 32 / g.P;
+    const int B = hdr->B, Bcur = hdr->Bcur, cur = hdr->cur;
+    const int cap = a.cand_cap;
+
+    float* s_T2 = reinterpret_cast<float*>(smem_raw);                // [IREC_T2_LEN]
+    float* s_csc = s_T2 + IREC_T2_LEN;                               // [cap]
+    int32_t* s_cid = reinterpret_cast<int32_t*>(s_csc + cap);        // [cap]
+    float* s_gmax = reinterpret_cast<float*>(s_cid + cap);           // [GP2_THREADS]
+    float* s_wsc = s_gmax + GP2_THREADS;                             // [32]
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);         // [32]
+    int32_t* s_list = s_wid + 32;                                    // [TOPK_CAP]
+    int32_t* s_ctl = s_list + TOPK_CAP;                              // [4]
+    int32_t* s_cnt = s_ctl + 4;                                      // [1] candidate count
+    float* s_tau = reinterpret_cast<float*>(s_cnt + 1);              // [1]
+    uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_tau + 1) + 2;     // [32] 4 * dlog(h_b)
+
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.T2);
+        float4* dst = reinterpret_cast<float4*>(s_T2);
+        for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
+    }
+    if (tid == 0) { *s_cnt = 0; *s_tau = __int_as_float(0xff800000); }
+    const int32_t* hs = st_hsum(a.state, cur, B, g.DP);
+    if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs[tid]) - 1)) : 0u;
+
+    const float4* sa4 = reinterpret_cast<const float4*>(st_arr(a.state, 4, g.DP));
+    const float4* A4 = reinterpret_cast<const float4*>(st_arr(a.state, 5, g.DP));
+    const float4* E4 = reinterpret_cast<const float4*>(st_arr(a.state, 6, g.DP));
+    const float4* M4 = reinterpret_cast<const float4*>(st_arr(a.state, 7, g.DP));
+    const float4* beams4 = reinterpret_cast<const float4*>(st_beams(a.state, cur, B, g.DP));
+    const TfStream st = tf_stream_seeded(hdr->seed + a.t, hdr->seed + a.t);
+    const int lg = lane & (g.P - 1);
+    const char* T2b = reinterpret_cast<const char*>(s_T2);
+    constexpr int HB = R2Pass<BMAX>::HB;
+
+    // contiguous range of sample groups per CTA
+    const int64_t nsg = (a.s_end - a.s_begin + g.SPW - 1) / g.SPW;
+    const int64_t per = (nsg + gridDim.x - 1) / gridDim.x;
+    const int64_t sg0 = (int64_t)blockIdx.x * per, sg1 = min(nsg, sg0 + per);
+    __syncthreads();
+
+    for (int64_t base = sg0; base < sg1; base += nwarps) {
+        const int64_t sg = base + warp;
+        const int64_t s = a.s_begin + sg * g.SPW + lane / g.P;
+        const bool warp_valid = sg < sg1;
+        const bool valid = warp_valid && s < a.s_end;
+        const uint64_t s_eff = (uint64_t)(valid ? s : a.s_begin);
+        const uint64_t jb[1] = { s_eff * (uint64_t)g.D + (uint64_t)(32 * lg) };
+        const uint32_t row[1] = { 0u };
+        const float tau = *s_tau;
+#pragma unroll 1
+        for (int boff = 0; boff < BMAX; boff += HB) {
+            if (boff >= Bcur) break;
+            float acc[1][HB];
+#pragma unroll
+            for (int b = 0; b < HB; ++b) acc[0][b] = 0.f;
+            r2_score_chunk<HB, 1, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2), g.DP >> 2, g.P, lg, st,
+                                         jb, nullptr, row, acc);
+            float v[HB];
+#pragma unroll
+            for (int b = 0; b < HB; ++b) v[b] = acc[0][b];
+            const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, (int)a.s_end, warp_valid };
+            r2_tree_store<HB, HB, HB, 0, Gp2Sink>(v, g.P, lane, (int)s, 0, sink);
+        }
+        __syncthreads();
+        const int cnt = *s_cnt;
+        if (cnt > B) {
+            const int Kout = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+            if (tid < Kout) { s_csc[tid] = s_wsc[tid]; s_cid[tid] = s_wid[tid]; }
+            if (tid == 0) { *s_cnt = Kout; if (Kout == B) *s_tau = s_wsc[Kout - 1]; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const int cnt = *s_cnt;
+    const int Kout = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+    if (tid < Kout) {
+        irec_record_t r;
+        const int f = s_wid[tid];
+        r.score = s_wsc[tid]; r.s = f / Bcur; r.b = f - r.s * Bcur; r.pad = 0;
+        a.out_rec[(size_t)blockIdx.x * B + tid] = r;
+    }
+    if (tid == 0) a.out_cnt[blockIdx.x] = Kout;
+}
+
 // merge: records laid out as n_lists lists of stride `stride`, list i has cnt[i] valid entries
 // (cnt == nullptr: every list is full with `stride` entries... use n_valid).  Output best B, sorted.
 __global__ void __launch_bounds__(256) k_topb_merge(const irec_record_t* __restrict__ rec, const int32_t* __restrict__ cnt,
@@ -936,6 +1059,61 @@ static int gp_score_grid(int D, int64_t n_samples)
     return (int)grid;
 }
 
+static size_t gp2_score_smem(int cand_cap)
+{
+    return sizeof(float) * ((size_t)IREC_T2_LEN + (size_t)cand_cap + GP2_THREADS + 32) +
+           sizeof(int32_t) * ((size_t)cand_cap + 32 + TOPK_CAP + 4 + 4 + 32) + 16;
+}
+static int gp2_cand_cap(int D, int bmax)
+{
+    const BeamGeom g = make_geom(D);
+    return (GP2_THREADS / 32) * g.SPW * bmax + 64;
+}
+static int gp2_score_grid(int D, int64_t n_samples)
+{
+    const BeamGeom g = make_geom(D);
+    const int64_t nsg = (n_samples + g.SPW - 1) / g.SPW;
+    int64_t grid = (nsg + (GP2_THREADS / 32) - 1) / (GP2_THREADS / 32);       // at least one round of work per CTA
+    const int cap = irec_device().sm_count;                                   // one CTA per SM (120 KB table + 512 threads)
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return (int)grid;
+}
+static bool gp_use_v2(int D, int bmax)
+{
+    const char* e = getenv("IREC_GP_V1");
+    if (e && e[0] == '1') return false;
+    return D <= 1024 && gp2_score_smem(gp2_cand_cap(D, bmax)) <= (size_t)irec_device().max_smem_optin;
+}
+template <int BMAX>
+static int launch_gp2_score_t(const Score2Args& a, int grid, size_t smem, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(k_gp_score_topb2<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)irec_device().max_smem_optin) != cudaSuccess)
+            return IREC_E_CUDA;
+        attr_done = true;
+    }
+    k_gp_score_topb2<BMAX><<<grid, GP2_THREADS, smem, s>>>(a);
+    irec_count_launch();
+    return IREC_OK;
+}
+static int launch_gp2_score(int bmax, const Score2Args& a, int grid, size_t smem, cudaStream_t s)
+{
+    switch (bmax) {
+        case 1: return launch_gp2_score_t<1>(a, grid, smem, s);
+        case 2: return launch_gp2_score_t<2>(a, grid, smem, s);
+        case 4: return launch_gp2_score_t<4>(a, grid, smem, s);
+        case 8: return launch_gp2_score_t<8>(a, grid, smem, s);
+        case 10: return launch_gp2_score_t<10>(a, grid, smem, s);
+        case 16: return launch_gp2_score_t<16>(a, grid, smem, s);
+        case 20: return launch_gp2_score_t<20>(a, grid, smem, s);
+        case 32: return launch_gp2_score_t<32>(a, grid, smem, s);
+    }
+    return IREC_E_INVALID;
+}
+
 template <int BMAX>
 static int launch_gp_score_t(const ScoreArgs& a, int grid, size_t smem, cudaStream_t s)
 {
@@ -1065,12 +1243,22 @@ int irec_beam_step_score(void* state, int D, int B, int t, int64_t s_begin, int6
     int32_t* g_id = reinterpret_cast<int32_t*>(g_sc + (size_t)grid_max * 32 + 64);
 
     const int64_t ns = s_end > s_begin ? s_end - s_begin : 0;
-    const int grid = gp_score_grid(D, ns);
-    const int cap = gp_cand_cap(D, bmax);
-    ScoreArgs a;
-    a.state = state; a.t = t; a.T = irec_device().d_T; a.s_begin = s_begin; a.s_end = s_end;
-    a.out_rec = rec; a.out_cnt = cnt; a.cand_cap = cap;
-    int rc = launch_gp_score(bmax, a, grid, gp_score_smem(cap), s);
+    int grid, rc;
+    if (gp_use_v2(D, bmax)) {
+        grid = gp2_score_grid(D, ns);
+        const int cap = gp2_cand_cap(D, bmax);
+        Score2Args a;
+        a.state = state; a.t = t; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4; a.s_begin = s_begin; a.s_end = s_end;
+        a.out_rec = rec; a.out_cnt = cnt; a.cand_cap = cap;
+        rc = launch_gp2_score(bmax, a, grid, gp2_score_smem(cap), s);
+    } else {
+        grid = gp_score_grid(D, ns);
+        const int cap = gp_cand_cap(D, bmax);
+        ScoreArgs a;
+        a.state = state; a.t = t; a.T = irec_device().d_T; a.s_begin = s_begin; a.s_end = s_end;
+        a.out_rec = rec; a.out_cnt = cnt; a.cand_cap = cap;
+        rc = launch_gp_score(bmax, a, grid, gp_score_smem(cap), s);
+    }
     if (rc != IREC_OK) return irec_fail(rc, "beam_step_score: launch failed");
     // Bcur is only known on the device: the merge kernel reads ids as s*Bcur+b with the header's Bcur
     k_topb_merge<<<1, 256, 0, s>>>(rec, cnt, grid, B, &reinterpret_cast<BeamStateHdr*>(state)->Bcur, 0, B, out_records,

@@ -32,6 +32,18 @@ __device__ __forceinline__ uint32_t r2_exp4(const uint16_t* __restrict__ dl4, ui
     return (uint32_t)__ldg(dl4 + u % IREC_ORD);
 }
 
+// In-place version of the two-choice bank assignment (no precomputed table): the 32 lanes of a gather instruction find
+// out with ONE match.any which of them share a bank (all beams add the same c_b, so the pattern holds for every beam of
+// the instruction); the odd-ranked lanes of every group switch to the second copy of T2 (+10006 words = 22 banks on).
+// Random banks cost 3.5 wavefronts per gather, this one-shot rule 2.7 (the offline greedy of k_r2_exps: 2.2).
+// All 32 lanes of the warp must call it.  Same values either way (T2[a] == T2[a + 10006]).
+__device__ __forceinline__ uint32_t r2_spread_banks(uint32_t ad)
+{
+    const uint32_t peers = __match_any_sync(0xffffffffu, (ad >> 2) & 31u);
+    const uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    return ad + ((rank & 1u) ? 4u * IREC_ORD : 0u);
+}
+
 // exponent-table entry: 4 x uint16 word offsets a' (a or a + 10006) -> byte offsets into T2
 __device__ __forceinline__ void r2_unpack(const uint2 c, uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3)
 {
@@ -49,7 +61,7 @@ struct R2Group {   // beams per inner batch: G * 4 independent gathers in flight
 //   j_base[k] = s_k * D + first dim of the chunk;  q0 = float4 index of the chunk's first quad
 //   row[k]: sample s_k's row of the precomputed exponent table (4 x uint16 per quad, CI layout) or nullptr
 //           (then the exponents come from Philox + dl4 in place)
-template <int BMAX, int NS, bool TAB>
+template <int BMAX, int NS, bool TAB, bool SPREAD = false>   // SPREAD: in-place two-choice bank assignment (TAB == false only)
 __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, const uint16_t* __restrict__ dl4,
                                                const uint32_t* __restrict__ cb4,
                                                const float4* __restrict__ sa4, const float4* __restrict__ A4,
@@ -84,6 +96,10 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
                 const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
                 ad[k][0] = r2_exp4(dl4, u.x); ad[k][1] = r2_exp4(dl4, u.y);
                 ad[k][2] = r2_exp4(dl4, u.z); ad[k][3] = r2_exp4(dl4, u.w);
+                if (SPREAD) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ad[k][e] = r2_spread_banks(ad[k][e]);
+                }
             }
         }
         const int qi = q0 + iq * P;

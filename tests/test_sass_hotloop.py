@@ -45,33 +45,37 @@ def test_quantile_gathers_stay_software_pipelined(built):
     gather_line = 1 + next(i for i, l in enumerate(src) if "tv[g][e] = *reinterpret_cast<const float*>(T2b + (ad[k][e] + cb[g]));" in l)
     with tempfile.TemporaryDirectory() as tmp:
         ins = _kernel_sass(tmp)
-    # the unrolled loop body = the longest run of instructions attributed to the scoring chunk (source lines of r2_score_chunk)
+    # unrolled loop bodies = long runs of instructions attributed to the scoring chunk (source lines of r2_score_chunk);
+    # the kernel holds several instances (table / in-place exponents, 1 / 10 beams per pass): the hot one is the
+    # table-driven pass of 10 beams x 3 samples = the run with >= 100 gathers whose neighbourhood loads 8-byte exponent-table entries (and has no MATCH of the in-place bank assignment)
     lo, hi = gather_line - 50, gather_line + 20
-    best, i = (0, 0, 0), 0
+    runs, i = [], 0
     while i < len(ins):
         if lo <= ins[i][0] <= hi:
             j = i
-            while j < len(ins) and (lo <= ins[j][0] <= hi or ins[j][0] in range(28, 42)):
+            while j < len(ins) and (lo <= ins[j][0] <= hi or ins[j][0] in range(28, 60)):
                 j += 1
-            if j - i > best[0]:
-                best = (j - i, i, j)
+            if j - i > 200:
+                runs.append((ins[i:j], ins[max(0, i - 120):i] + ins[j:j + 120]))
             i = j
         else:
             i += 1
-    body = ins[best[1]:best[2]]
-    assert len(body) > 400, "hot loop not found in the SASS"
-    dist = []
-    for k, (line, text) in enumerate(body):
-        m = re.match(r"LDS R(\d+), ", text)
-        if not (m and line == gather_line):
-            continue
-        reg = re.compile(r"\bR" + m.group(1) + r"\b")
-        for n in range(k + 1, len(body)):
-            ops = body[n][1].split(",", 1)
-            if len(ops) > 1 and reg.search(ops[1]):
-                dist.append(n - k)
-                break
-    assert len(dist) >= 60, len(dist)
-    local = sum(1 for _, t in body if re.match(r"(LDL|STL)", t))
+    hot = []
+    for body, around in runs:
+        dist = []
+        for k, (line, text) in enumerate(body):
+            m = re.match(r"LDS R(\d+), ", text)
+            if not (m and line == gather_line):
+                continue
+            reg = re.compile(r"\bR" + m.group(1) + r"\b")
+            for n in range(k + 1, len(body)):
+                ops = body[n][1].split(",", 1)
+                if len(ops) > 1 and reg.search(ops[1]):
+                    dist.append(n - k)
+                    break
+        if len(dist) >= 100 and any("LDG.E.64" in t for _, t in body + around) and not any("MATCH" in t for _, t in body + around):      # 8-byte exponent-table entries
+            hot.append((dist, sum(1 for _, t in body if re.match(r"(LDL|STL)", t))))
+    assert len(hot) == 1, [len(d) for d, _ in hot]
+    dist, local = hot[0]
     assert statistics.median(dist) >= 10, (statistics.median(dist), sorted(dist)[:10])
     assert local <= 4, local
