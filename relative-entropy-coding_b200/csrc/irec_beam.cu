@@ -533,7 +533,12 @@ __global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
 // computed in place (S is far too large for a table here: 2^24 samples x 64 dims), in-place two-choice bank assignment
 // (r2_spread_banks), beams in passes of R2Pass::HB.  First generation (profiles/r1_gp_score_ncu.md): 255 registers,
 // three IMADs per candidate-dim, 3.5 shared-memory wavefronts per gather, data pipe 74 % busy.  Same scores bit for bit.
-#define GP2_THREADS 512
+#ifndef GP2_THREADS
+#define GP2_THREADS 384
+#endif
+#ifndef GP2_NS
+#define GP2_NS 2            // sample groups per warp and round: a beam quad read from global memory serves 8 candidate-dims
+#endif            // (A/B at S = 2^24, one GPU: 512 threads x 1 group 118 ms, 384 x 2 108 ms, 512 x 2 109 ms, 256 x 3 137 ms)
 struct Score2Args {
     void* state; int t; const float* T2; const uint16_t* dl4;
     int64_t s_begin, s_end;
@@ -542,11 +547,11 @@ struct Score2Args {
 };
 struct Gp2Sink {
     float* s_csc; int32_t* s_cid; int32_t* s_cnt;
-    float tau; int Bcur, boff; int s_end; bool warp_valid;
+    float tau; int Bcur, boff; int s_hi;      // s_hi: first sample beyond this CTA's range
     __device__ __forceinline__ void operator()(int sk, int b, float x, bool dup) const
     {
         b += boff;
-        if (dup || !warp_valid || b >= Bcur || sk >= s_end) return;
+        if (dup || b >= Bcur || sk >= s_hi) return;
         const float v = (x == x) ? x : __int_as_float(0xff800000);
         if (v >= tau) {
             const int pos = atomicAdd(s_cnt, 1);
@@ -608,28 +613,37 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_score_topb2(const Score2A
     const int64_t sg0 = (int64_t)blockIdx.x * per, sg1 = min(nsg, sg0 + per);
     __syncthreads();
 
-    for (int64_t base = sg0; base < sg1; base += nwarps) {
-        const int64_t sg = base + warp;
-        const int64_t s = a.s_begin + sg * g.SPW + lane / g.P;
-        const bool warp_valid = sg < sg1;
-        const bool valid = warp_valid && s < a.s_end;
-        const uint64_t s_eff = (uint64_t)(valid ? s : a.s_begin);
-        const uint64_t jb[1] = { s_eff * (uint64_t)g.D + (uint64_t)(32 * lg) };
-        const uint32_t row[1] = { 0u };
+    const int64_t s_hi64 = min(a.s_end, a.s_begin + sg1 * g.SPW);
+    const int s_hi = (int)s_hi64;
+    for (int64_t base = sg0; base < sg1; base += (int64_t)nwarps * GP2_NS) {
+        uint64_t jb[GP2_NS];
+        uint32_t row[GP2_NS];
+#pragma unroll
+        for (int k = 0; k < GP2_NS; ++k) {
+            const int64_t s = a.s_begin + (base + warp + (int64_t)k * nwarps) * g.SPW + lane / g.P;
+            const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // groups beyond the range: clamped, not stored
+            jb[k] = s_eff * (uint64_t)g.D + (uint64_t)(32 * lg);
+            row[k] = 0u;
+        }
+        const int s_first = (int)(a.s_begin + (base + warp) * g.SPW + lane / g.P);
         const float tau = *s_tau;
 #pragma unroll 1
         for (int boff = 0; boff < BMAX; boff += HB) {
             if (boff >= Bcur) break;
-            float acc[1][HB];
+            float acc[GP2_NS][HB];
 #pragma unroll
-            for (int b = 0; b < HB; ++b) acc[0][b] = 0.f;
-            r2_score_chunk<HB, 1, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2), g.DP >> 2, g.P, lg, st,
-                                         jb, nullptr, row, acc);
-            float v[HB];
+            for (int k = 0; k < GP2_NS; ++k)
 #pragma unroll
-            for (int b = 0; b < HB; ++b) v[b] = acc[0][b];
-            const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, (int)a.s_end, warp_valid };
-            r2_tree_store<HB, HB, HB, 0, Gp2Sink>(v, g.P, lane, (int)s, 0, sink);
+                for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
+            r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2), g.DP >> 2,
+                                                    g.P, lg, st, jb, nullptr, row, acc);
+            float v[GP2_NS * HB];
+#pragma unroll
+            for (int k = 0; k < GP2_NS; ++k)
+#pragma unroll
+                for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
+            const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, s_hi };
+            r2_tree_store<GP2_NS * HB, GP2_NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
         }
         __syncthreads();
         const int cnt = *s_cnt;
@@ -1067,13 +1081,13 @@ static size_t gp2_score_smem(int cand_cap)
 static int gp2_cand_cap(int D, int bmax)
 {
     const BeamGeom g = make_geom(D);
-    return (GP2_THREADS / 32) * g.SPW * bmax + 64;
+    return (GP2_THREADS / 32) * GP2_NS * g.SPW * bmax + 64;
 }
 static int gp2_score_grid(int D, int64_t n_samples)
 {
     const BeamGeom g = make_geom(D);
     const int64_t nsg = (n_samples + g.SPW - 1) / g.SPW;
-    int64_t grid = (nsg + (GP2_THREADS / 32) - 1) / (GP2_THREADS / 32);       // at least one round of work per CTA
+    int64_t grid = (nsg + (GP2_THREADS / 32) * GP2_NS - 1) / ((GP2_THREADS / 32) * GP2_NS);       // at least one round of work per CTA
     const int cap = irec_device().sm_count;                                   // one CTA per SM (120 KB table + 512 threads)
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
