@@ -74,6 +74,11 @@ int irec_is_normal_stream(int64_t seed, int64_t start, int64_t n, float* out, vo
  *   tfd.Normal.sample(n, seed=op_seed) before scale/shift -- the candidate buffers of the rejection sampler's
  *   NaiveSampleGenerator (rec/coding/sample_generator.py:53-66) */
 int irec_normal_stream_seeded(int64_t global_seed, int64_t op_seed, int64_t start, int64_t n, float* out, void* stream);
+/*   irec_uniform_int_stream : tf.random.uniform(shape, lo, hi, dtype=int32, seed=op_seed) after set_seed(global_seed):
+ *   lo + u32 % (hi - lo) over the same Philox stream -- the group / sample assignments of the rejection sampler's
+ *   PseudoSampleGenerator (rec/coding/sample_generator.py:84-93); irec_beam_uniform_int is the (1, 10007) case */
+int irec_uniform_int_stream(int64_t global_seed, int64_t op_seed, int32_t lo, int32_t hi, int64_t start, int64_t n, int32_t* out,
+                            void* stream);
 /* HOST (tests): the table-driven float64 log / sincos behind the Box-Muller candidates (csrc/irec_boxmuller.cuh),
  * evaluated on the host with the operation sequence of the device, for m[i] = the 23 mantissa bits of a Philox word:
  * logf_out = float(log(max(Uint32ToFloat(m), 1e-7f))), (sin_out, cos_out) = float(sin/cos(float(2 pi Uint32ToFloat(m)))).

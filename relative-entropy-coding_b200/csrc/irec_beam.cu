@@ -795,6 +795,17 @@ __global__ void k_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t*
     }
 }
 
+// tf.random.uniform(shape, lo, hi, dtype=int32, seed=op_seed) after tf.random.set_seed(global_seed): lo + u32 % (hi - lo)
+__global__ void k_uniform_int_stream(TfStream st, uint32_t lo, uint32_t range, int64_t start, int64_t n, int32_t* out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = (uint64_t)(start + i);
+        const uint4 u = tf_stream_group(st, j >> 2);
+        const uint32_t v[4] = { u.x, u.y, u.z, u.w };
+        out[i] = (int32_t)(lo + v[j & 3] % range);
+    }
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -1166,6 +1177,18 @@ int irec_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out, voi
     k_beam_uniform_int<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(q, start, n, out);
     irec_count_launch();
     return irec_check_launch("k_beam_uniform_int");
+}
+
+int irec_uniform_int_stream(int64_t global_seed, int64_t op_seed, int32_t lo, int32_t hi, int64_t start, int64_t n, int32_t* out,
+                            void* stream)
+{
+    IREC_ENSURE_INIT();
+    if (hi <= lo) return irec_fail(IREC_E_INVALID, "uniform_int_stream: need lo < hi");
+    if (n <= 0) return IREC_OK;
+    k_uniform_int_stream<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(
+        tf_stream_seeded(global_seed, op_seed), (uint32_t)lo, (uint32_t)(hi - lo), start, n, out);
+    irec_count_launch();
+    return irec_check_launch("k_uniform_int_stream");
 }
 
 int irec_kl_naux(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,

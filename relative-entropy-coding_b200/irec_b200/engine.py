@@ -249,6 +249,14 @@ def normal_stream_seeded(global_seed, op_seed, start, n, device="cuda"):
     return out
 
 
+def uniform_int_stream(global_seed, op_seed, lo, hi, start, n, device="cuda"):
+    """tf.random.uniform(..., lo, hi, int32, seed=op_seed)[start : start + n] after tf.random.set_seed(global_seed)"""
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    N.check(N.lib().irec_uniform_int_stream(int(global_seed), int(op_seed), int(lo), int(hi), int(start), int(n), N.ptr(out),
+                                            N.stream_ptr()), "irec_uniform_int_stream")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # candidate-range sharded beam coder for ONE block (large S; 1..8 GPUs).  Every rank holds a replica
 # of the block state; per partition each rank scores its contiguous candidate range, the per-rank

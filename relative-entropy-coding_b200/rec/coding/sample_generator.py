@@ -4,7 +4,7 @@
 `coder.sample((buffer,), seed=seed)` after `tf.random.set_seed(seed)` is the float32 tf.random.normal stream with
 (global seed, op seed) = (seed, seed), times scale plus loc; the stream is regenerated on the GPU by
 `irec_normal_stream_seeded` (Philox4x32-10 + Box-Muller, bit-compatible restatement), so encoder and decoder see the
-same candidates.  The PseudoSampleGenerator (reference :69-133) is not built."""
+same candidates.  PseudoSampleGenerator (reference :69-133): a few true samples recombined per random group of dims."""
 import abc
 import math
 
@@ -58,3 +58,54 @@ class NaiveSampleGenerator(SampleGenerator):
 
     def generate_index(self, i, coder, seed):
         return self._buffer(coder, seed, first=int(i), count=1)[0]      # counter-based: only the asked sample is generated
+
+
+class PseudoSampleGenerator(SampleGenerator):
+    """reference :69-133 -- `n_true_samples` real draws of the coder; the dims are thrown into `n_groups` random groups and
+    pseudo-sample i takes, for every group, the values of one randomly assigned true sample.  All three random tensors come
+    from the SAME Philox stream (every op is called with seed=seed after set_seed(seed)), restated by
+    irec_normal_stream_seeded / irec_uniform_int_stream."""
+
+    def __init__(self, sample_buffer_size, n_true_samples=50, n_groups=50, **kwargs):
+        self.sample_buffer_size = int(sample_buffer_size)
+        self.n_true_samples = int(n_true_samples)
+        self.n_groups = int(n_groups)
+        self.samples = None
+        self.group_assignments = None
+        self.sample_assignments = None
+
+    def _draw(self, coder, seed):
+        loc, scale = E._f32c(coder.loc, "cuda"), E._f32c(coder.scale, "cuda")
+        d = loc.numel()
+        z = E.normal_stream_seeded(seed, seed, 0, self.n_true_samples * d, device=loc.device)
+        self.samples = z.reshape((self.n_true_samples,) + tuple(loc.shape)) * scale + loc
+        self.group_assignments = E.uniform_int_stream(seed, seed, 0, self.n_groups, 0, d, device=loc.device).long()      # [d]
+        self.sample_assignments = E.uniform_int_stream(seed, seed, 0, self.n_true_samples, 0,
+                                                       self.n_groups * self.sample_buffer_size,
+                                                       device=loc.device).long().reshape(self.n_groups, self.sample_buffer_size)
+        return loc, scale
+
+    def get_ratios(self, target, coder, seed):
+        loc, scale = self._draw(coder, seed)
+        t_loc, t_scale = E._f32c(target.loc, "cuda"), E._f32c(target.scale, "cuda")
+        ratios = (normal_log_prob(self.samples, t_loc, t_scale) - normal_log_prob(self.samples, loc, scale))
+        flat = ratios.reshape(self.n_true_samples, -1)                                          # [n_true, d]
+        mask = torch.nn.functional.one_hot(self.group_assignments, self.n_groups).to(flat.dtype)  # [d, n_groups]
+        group_ratios = flat @ mask                                                              # [n_true, n_groups]
+        # ratio of pseudo-sample i = sum_g group_ratios[sample_assignments[g, i], g]
+        g = torch.arange(self.n_groups, device=flat.device)[:, None]
+        return group_ratios[self.sample_assignments, g].sum(dim=0)
+
+    def _assemble(self, i):
+        group_indices = self.sample_assignments[:, int(i)]                    # [n_groups] true-sample index per group
+        per_dim = group_indices[self.group_assignments]                       # [d]
+        flat = self.samples.reshape(self.n_true_samples, -1)
+        d = torch.arange(flat.shape[1], device=flat.device)
+        return flat[per_dim, d].reshape(self.samples.shape[1:])
+
+    def get_index(self, i):
+        return self._assemble(i)
+
+    def generate_index(self, i, coder, seed):
+        self._draw(coder, seed)
+        return self._assemble(i)

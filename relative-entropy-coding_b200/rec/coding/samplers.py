@@ -69,12 +69,10 @@ class RejectionSampler(Sampler):
 
     def __init__(self, sample_buffer_size, r_buffer_size, use_pseudo_sampler=False, name="rejection_sampler", **kwargs):
         super().__init__(name=name, **kwargs)
-        from rec.coding.sample_generator import NaiveSampleGenerator
-        if use_pseudo_sampler:
-            raise NotImplementedError("PseudoSampleGenerator (reference sample_generator.py:69-133) is not built")
+        from rec.coding.sample_generator import NaiveSampleGenerator, PseudoSampleGenerator
         self.sample_buffer_size = int(sample_buffer_size)
         self.r_buffer_size = int(r_buffer_size)
-        self.sample_generator = NaiveSampleGenerator(self.sample_buffer_size)
+        self.sample_generator = (PseudoSampleGenerator if use_pseudo_sampler else NaiveSampleGenerator)(self.sample_buffer_size)
         self.average_count = 0.
         self._initialized = False
         self.acceptance_probabilities = np.zeros(self.r_buffer_size, dtype=np.float64)

@@ -79,8 +79,9 @@ def test_api_surface(built):
     assert b.simple_hash([[3, 5]]).tolist() == [O.simple_hash([3, 5])]
     r = RejectionSampler(sample_buffer_size=10, r_buffer_size=20)      # reference samplers.py:106
     assert isinstance(r, Sampler) and r.sample_buffer_size == 10 and r.r_buffer_size == 20
-    with pytest.raises(NotImplementedError):
-        RejectionSampler(sample_buffer_size=10, r_buffer_size=20, use_pseudo_sampler=True)
+    from rec.coding.sample_generator import PseudoSampleGenerator
+    assert isinstance(RejectionSampler(sample_buffer_size=10, r_buffer_size=20, use_pseudo_sampler=True).sample_generator,
+                      PseudoSampleGenerator)
     with pytest.raises(CodingError):
         encode_gaussian_importance_sample(None, None, None, None, 3., 1, alpha=0.5)
     with pytest.raises(CodingError):

