@@ -30,6 +30,7 @@ CONFIGS = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--max-aux", type=int, default=256, help="pipelined compress (no host sync between levels); 0 = level by level")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as g
@@ -48,7 +49,7 @@ def main():
             torch.cuda.synchronize()
             l0 = N.launch_count()
             t0 = time.perf_counter()
-            block_indices, latents = model.compress(42, coder, file_path=path, image_shape=c["image"])
+            block_indices, latents = model.compress(42, coder, file_path=path, image_shape=c["image"], max_aux=args.max_aux or None)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             decoded = model.decompress(coder, file_path=path)
@@ -67,7 +68,7 @@ def main():
                           "encode_ms": 1e3 * min(enc), "decode_ms": 1e3 * min(dec), "candidates_per_sec": cand / min(enc),
                           "partitions_per_sec": sum(n_aux) / min(enc), "file_bytes": os.path.getsize(path),
                           "bits_per_dim_file": 8 * os.path.getsize(path) / dims,
-                          "bits_per_dim_index_stream": sum(n_aux) * np.log2(S) / dims, "gpu_launches": int(launches),
+                          "bits_per_dim_index_stream": sum(n_aux) * np.log2(S) / dims, "gpu_launches": int(launches), "pipelined_levels": bool(args.max_aux),
                           "decode_bit_exact": True}), flush=True)
 
 

@@ -103,6 +103,42 @@ class BeamSearchCoder(GaussianCoder):
                                             offsets, nb, max_dim, seed)
         return nest(indices), sample.reshape(shape)
 
+    def encode_lazy(self, target_dist, coding_dist, seed, max_aux=256):
+        """`encode` without a host synchronisation: the caller promises that no coder-block needs more than `max_aux`
+        auxiliary variables (KL <= max_aux * kl_per_partition per block), so the sizing pre-pass and its device->host
+        read are skipped, the kernel is launched and (get_indices, sample) returned at once; `sample` is valid in stream
+        order, `get_indices()` reads the index lists back and raises CodingError if the promise did not hold (then the
+        sample was NOT valid and everything computed from it must be redone through `encode`).  Lets the sequential levels
+        of a model (resnet_vae.py:821-826) be enqueued back to back."""
+        self._check_ratios()
+        tl, ts = _dist_tensors(target_dist)
+        pl, ps = _dist_tensors(coding_dist)
+        shape = tl.shape
+        for t in (ts, pl, ps):
+            if t.shape != shape:
+                raise CodingError("All tensor arguments supplied to split must have the same batch dimensions!")
+        if shape[0] != 1:
+            raise CodingError("For encoding, batch size must be 1.")
+        n = tl.numel()
+        perm = self._permutation(n, seed, tl.device) if self.block_size is not None else None
+        offsets, nb, max_dim = self._block_structure(n, tl.device)
+        with self._ratios_ctx(tl.device):
+            pend = E.beam_encode_blocks(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), perm, offsets, nb,
+                                        max_dim, self.kl_per_partition, self.n_samples, self.n_beams, seed,
+                                        max_aux=int(max_aux), lazy=True)
+        block_size = self.block_size
+        return (lambda: pend.indices() if block_size is not None else pend.indices()[0]), pend.sample.reshape(shape)
+
+    def _block_structure(self, n, device):
+        """block offsets of a tensor of n dims (cached: the same shapes recur for every level and image)"""
+        key = (int(n), self.block_size, str(device))
+        cache = self.__dict__.setdefault("_offsets_cache", {})
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = E.make_block_offsets(n, self.block_size, device)
+        return cache[key]
+
     def decode_batch(self, coding_dist, indices, seed):
         self._check_ratios()
         pl, ps = _dist_tensors(coding_dist)

@@ -24,18 +24,33 @@ class LatentHierarchy:
         self.ladder = ladder
 
     # -- resnet_vae.py:803-836 / large_2_level_vae.py:406-419 -------------------------------------------------------
-    def compress(self, seed, coder, file_path=None, image_shape=(32, 32, 3), max_index=None):
+    def compress(self, seed, coder, file_path=None, image_shape=(32, 32, 3), max_index=None, max_aux=None):
         """codes every level in order; returns (block_indices, latents).  With file_path the index stream is written as
-        a `.rec` file (rec/io/utils.py:7-106); max_index defaults to the coder's alphabet size minus one."""
+        a `.rec` file (rec/io/utils.py:7-106); max_index defaults to the coder's alphabet size minus one.
+        max_aux: promise that no coder-block needs more auxiliary variables than this -- the levels are then enqueued back
+        to back without a host synchronisation (coder.encode_lazy; the next level's prior only needs the latent ON THE
+        DEVICE) and the index lists are read back at the end; a broken promise raises CodingError, call again without it."""
         block_indices, latents = [], []
+        pipelined = max_aux is not None and hasattr(coder, "encode_lazy")
+        pending = []
         for level in range(self.ladder.n_levels):
             prior = self.ladder.prior(level, latents)
             posterior = self.ladder.posterior(level, latents)
+            if pipelined:
+                get_indices, latent = coder.encode_lazy(posterior, prior, seed=seed, max_aux=max_aux)
+                pending.append(get_indices)
+                latents.append(latent)
+                continue
             indices, latent = coder.encode(posterior, prior, seed=seed)
             if coder.block_size is None:
                 indices = [indices]                       # one coder-block
             block_indices.append([[int(i) for i in blk] for blk in indices])
             latents.append(latent)
+        for get_indices in pending:
+            indices = get_indices()
+            if coder.block_size is None:
+                indices = [indices]
+            block_indices.append([[int(i) for i in blk] for blk in indices])
         if file_path is not None:
             if max_index is None:
                 max_index = int(getattr(coder, "n_samples", 0)) or (1 + max(i for t in block_indices for b in t for i in b))

@@ -93,3 +93,26 @@ def test_lossless_resnet_vae_cifar_shape(cuda, tmp_path):
     ideal, actual = _run(cuda, tmp_path, [(16, 16, 32)] * 24, "c2", 20, 1.2, (32, 32, 3),
                          spot=[(0, [0, 8]), (11, [3]), (23, [8])])
     assert 0.1 < ideal < 20 and actual >= ideal
+
+
+def test_pipelined_compress_equals_level_by_level(cuda, tmp_path):
+    """LatentHierarchy.compress(max_aux=...) enqueues the levels without a host synchronisation (coder.encode_lazy): same
+    index lists, same latents, same file as the level-by-level loop; a max_aux that is too small is reported."""
+    import torch
+    from rec.coding import BeamSearchCoder
+    from rec.coding.utils import CodingError
+    from rec.models import LatentHierarchy, SyntheticLadder
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=1000)
+    model = LatentHierarchy(SyntheticLadder([(16, 16, 32)] * 5, recipe="c2", data_seed=9, device=cuda))
+    a_path, b_path = str(tmp_path / "a.rec"), str(tmp_path / "b.rec")
+    idx_a, lat_a = model.compress(42, coder, file_path=a_path)
+    idx_b, lat_b = model.compress(42, coder, file_path=b_path, max_aux=256)
+    assert idx_a == idx_b and all(torch.equal(x, y) for x, y in zip(lat_a, lat_b))
+    assert open(a_path, "rb").read() == open(b_path, "rb").read()
+    flat = BeamSearchCoder(kl_per_partition=3., n_beams=10, extra_samples=1.0)          # no block_size: one block per level
+    small = LatentHierarchy(SyntheticLadder([(4, 4, 8)] * 3, recipe="c2", data_seed=2, device=cuda))
+    i1, l1 = small.compress(7, flat)
+    i2, l2 = small.compress(7, flat, max_aux=64)
+    assert i1 == i2 and all(torch.equal(x, y) for x, y in zip(l1, l2))
+    with pytest.raises(CodingError):
+        model.compress(42, coder, max_aux=8)
