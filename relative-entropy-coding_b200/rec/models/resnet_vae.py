@@ -161,7 +161,13 @@ class BidirectionalResidualBlock(nn.Module):
                     latent = prior_loc + prior_scale * torch.randn_like(prior_loc)
                     self._initialized.fill_(True)
             elif encoder_args is not None:                                   # compression (:459-470)
-                indices, latent_nhwc = self.coder.encode(self.posterior, self.prior, **encoder_args)
+                args = dict(encoder_args)
+                max_aux = args.pop("max_aux", None)
+                if max_aux is not None and hasattr(self.coder, "encode_lazy"):
+                    # no host synchronisation: `indices` is a callable that reads the lists back later
+                    indices, latent_nhwc = self.coder.encode_lazy(self.posterior, self.prior, seed=args["seed"], max_aux=max_aux)
+                else:
+                    indices, latent_nhwc = self.coder.encode(self.posterior, self.prior, **args)
                 latent = _nchw(latent_nhwc)
             else:                                                            # decompression (:475-476)
                 latent = _nchw(self.coder.decode(self.prior, **decoder_args))
@@ -234,7 +240,10 @@ class BidirectionalResNetVAE(nn.Module):
 
     # -- :803-836 -------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def compress(self, image, seed, update_sampler=False):
+    def compress(self, image, seed, update_sampler=False, max_aux=None):
+        """max_aux (extension): promise that no coder-block needs more auxiliary variables than this; the blocks are
+        then coded without a host synchronisation between them (BeamSearchCoder.encode_lazy) and the index lists are
+        read back after the last block; CodingError if the promise is broken."""
         x = _nchw(image)
         n, _, h, w = x.shape
         t = self.first_infer_conv(x)
@@ -242,9 +251,13 @@ class BidirectionalResNetVAE(nn.Module):
             t = blk(t, inference_pass=True)
         t = self.generative_base(n, h, w)
         block_indices = []
+        enc_args = {"seed": seed, "update_sampler": update_sampler}
+        if max_aux is not None:
+            enc_args["max_aux"] = max_aux
         for blk in self.residual_blocks:
-            indices, t = blk(t, inference_pass=False, encoder_args={"seed": seed, "update_sampler": update_sampler})
+            indices, t = blk(t, inference_pass=False, encoder_args=enc_args)
             block_indices.append(indices)
+        block_indices = [ind() if callable(ind) else ind for ind in block_indices]
         rec = self._reconstruct(t)
         self.log_likelihood = self._likelihood(x, rec).mean()
         return block_indices, _nhwc(rec)

@@ -47,6 +47,9 @@ def test_rvae_compress_decompress(cuda):
         assert torch.allclose(blk.prior.loc, pl, atol=1e-5) and torch.allclose(blk.prior.scale, ps, atol=1e-5)
     assert torch.allclose(decoded, reconstruction + 0.5, atol=1e-4)
     assert decoded.shape == (1, 32, 32, 3)
+    # the blocks enqueued without a host synchronisation (encode_lazy): same code, same reconstruction
+    lazy_indices, lazy_reconstruction = model.compress(image, seed=42, max_aux=256)
+    assert lazy_indices == block_indices and torch.equal(lazy_reconstruction, reconstruction)
 
 
 def test_rvae_importance_sampler(cuda):
