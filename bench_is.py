@@ -73,7 +73,7 @@ def main():
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / args.reps
     launches = (N.launch_count() - l0) // args.reps
-    # device time of the coding kernel alone: the call also sizes max_aux (k_kl_naux + one D2H) and reads the indices back
+    # device time of the whole call: plan + candidate table + coding kernel, one packed D2H of the index rows
     ms_call = e0.elapsed_time(e1) / args.reps
 
     dec = E.is_decode_blocks(pl, ps, gather, offsets, nb, max_dim, SEED, indices)

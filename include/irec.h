@@ -35,6 +35,9 @@ extern "C" {
 #define IREC_BLK_TOO_LONG 2    /* n_aux > max_aux */
 
 int irec_version(void);
+/* sha256 (hex) of the sources, headers and compiler flags this binary was built from; __graft_entry__.build() compares
+ * it with the tree and rebuilds on mismatch */
+const char* irec_build_hash(void);
 const char* irec_last_error_string(void);
 
 /* One-time per-device tables: the 10006-entry float32 normal-quantile table
@@ -55,6 +58,9 @@ float irec_aux_ratio(int i);
  * more auxiliary variables than n reports IREC_BLK_TOO_LONG (the reference raises CodingError there,
  * coder.py:226-231). */
 int irec_set_thread_aux_ratios(const float* dev_ratios, int n);
+/* HOST: number of auxiliary variables the ratio table in force for the calling thread covers (the learned table's
+ * length, else the power-law table's 65536): an index list longer than this cannot be decoded (coder.py:226-231) */
+int irec_aux_ratio_len(void);
 
 /* HOST helpers restating TensorFlow's seed plumbing (python/framework/random_seed.py,
  * python/eager/context.py): op seed of the first unseeded random op after tf.random.set_seed(seed),
@@ -114,11 +120,14 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
 int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B);
 
 /* BeamSearchCoder.decode_block over nb blocks (beam_search_coder.py:124-148).  indices
- * [nb x max_aux] in partition order (the order encode returns), n_aux [nb]. */
+ * [nb x max_aux] in partition order (the order encode returns), n_aux [nb].  out_status [nb] (may be
+ * NULL): IREC_BLK_TOO_LONG for a block whose n_aux is negative, exceeds max_aux or exceeds the
+ * auxiliary-ratio table in force (the reference raises CodingError, coder.py:226-231); such a block
+ * decodes to NaN. */
 int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
                      const int64_t* block_offsets, int nb, int S, int64_t seed,
                      const int32_t* indices, int max_aux, const int32_t* n_aux,
-                     float* out_sample, void* stream);
+                     float* out_sample, int32_t* out_status, void* stream);
 
 /* ---- one partition at a time, candidate range [s_begin, s_end) -- the multi-GPU path ---------
  * The candidate index space of ONE coder-block is sharded: every rank holds a replica of the
@@ -185,9 +194,15 @@ int irec_is_decode_sample(const float* p_loc, const float* p_scale, int D, const
 /* GaussianCoder.encode_block / decode_block with an ImportanceSampler over nb blocks
  * (coder.py:493-584): auxiliary-variable loop with on-device conditioning (coder.py:141-171).
  * out_indices [nb x max_aux] int64 in the order the reference appends them (i = n_aux-1..1, final);
- * out_n_idx [nb] = max(n_aux, 1).  Blocks of at most 4096 dims.  These two calls synchronise
- * `stream` once (upload of the per-partition stream table). */
-size_t irec_is_block_workspace_bytes(int max_aux);
+ * out_n_idx [nb] = max(n_aux, 1).  Encode: blocks of at most 4096 dims.  Decode: out_status [nb] (may be
+ * NULL) flags blocks whose index count is < 1, > max_aux or > the ratio table in force with
+ * IREC_BLK_TOO_LONG (the reference raises IndexError / CodingError); they decode to NaN.  Both calls are
+ * asynchronous on `stream`. */
+size_t irec_is_block_workspace_bytes(int max_aux);            /* decode; minimum for encode */
+/* encode with room for the launch's candidate table: the S x D standard normals of every partition are the same for
+ * all coder-blocks of one size (the coding seed does not depend on the block, coder.py:523,538), so they are evaluated
+ * once per launch and streamed from L2; with only irec_is_block_workspace_bytes the kernel regenerates them per block */
+size_t irec_is_encode_workspace_bytes(int nb, int64_t max_block_dim, int64_t S, int max_aux);
 int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
                    const int64_t* gather_idx, const int64_t* block_offsets, int nb, int64_t max_block_dim,
                    float omega, int64_t S, int64_t seed,
@@ -196,7 +211,7 @@ int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc,
 int irec_is_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
                    const int64_t* block_offsets, int nb, int64_t max_block_dim, int64_t seed,
                    const int64_t* indices, int max_aux, const int32_t* n_idx,
-                   float* out_sample, void* workspace, size_t workspace_bytes, void* stream);
+                   float* out_sample, int32_t* out_status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 int64_t irec_launch_count(void);

@@ -14,13 +14,24 @@ LIB = os.path.join(OUT_DIR, "libirec_oracle.so")
 SRC = os.path.join(HERE, "irec_oracle.c")
 
 
+FLAGS = ["-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fexcess-precision=standard", "-Wall"]
+
+
+def _want() -> str:
+    import hashlib
+    with open(SRC, "rb") as f:
+        return hashlib.sha256(" ".join(FLAGS).encode() + f.read()).hexdigest()
+
+
 def build(force: bool = False) -> str:
+    """freshness by content (source + flags hash beside the library), not by mtime"""
     os.makedirs(OUT_DIR, exist_ok=True)
-    if (not force) and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    want, stamp = _want(), LIB + ".hash"
+    if (not force) and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == want:
         return LIB
-    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math",
-           "-fexcess-precision=standard", "-Wall", "-o", LIB, SRC, "-lm"]
-    subprocess.check_call(cmd)
+    subprocess.check_call(["gcc"] + FLAGS + ["-o", LIB, SRC, "-lm"])
+    with open(stamp, "w") as f:
+        f.write(want)
     return LIB
 
 

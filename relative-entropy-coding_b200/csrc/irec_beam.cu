@@ -56,12 +56,18 @@ __global__ void k_beam_decode(const float* __restrict__ p_loc, const float* __re
                               const int64_t* __restrict__ gidx, const int64_t* __restrict__ offs, int nb,
                               int64_t seed, const int32_t* __restrict__ indices, int max_aux,
                               const int32_t* __restrict__ n_aux_arr, const float* __restrict__ T,
-                              const float* __restrict__ ratio_tab, float* __restrict__ out)
+                              const float* __restrict__ ratio_tab, int ratio_len, float* __restrict__ out,
+                              int32_t* __restrict__ out_status)
 {
     for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
         const int64_t off = offs[blk];
         const int D = (int)(offs[blk + 1] - off);
-        const int n_aux = n_aux_arr[blk];
+        int n_aux = n_aux_arr[blk];
+        // an index list longer than the (learned) ratio table or than the row: the reference raises CodingError
+        // (coder.py:226-231); here the block decodes to NaN and is flagged
+        const bool bad = n_aux < 0 || n_aux > max_aux || n_aux > ratio_len;
+        if (threadIdx.x == 0 && out_status) out_status[blk] = bad ? IREC_BLK_TOO_LONG : IREC_BLK_OK;
+        if (bad) n_aux = 0;
         const int32_t* idx = indices + (size_t)blk * max_aux;
         const int nq = (D + 3) >> 2;
         for (int q = threadIdx.x; q < nq; q += blockDim.x) {
@@ -95,7 +101,7 @@ __global__ void k_beam_decode(const float* __restrict__ p_loc, const float* __re
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (d0 + e < D) out[gi[e]] = __fadd_rn(smp[e], pl[e]);
+                if (d0 + e < D) out[gi[e]] = bad ? __int_as_float(0x7fc00000) : __fadd_rn(smp[e], pl[e]);
         }
     }
 }
@@ -1206,14 +1212,15 @@ int irec_kl_naux(const float* t_loc, const float* t_scale, const float* p_loc, c
 int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
                      const int64_t* block_offsets, int nb, int S, int64_t seed,
                      const int32_t* indices, int max_aux, const int32_t* n_aux,
-                     float* out_sample, void* stream)
+                     float* out_sample, int32_t* out_status, void* stream)
 {
     IREC_ENSURE_INIT();
     (void)S;
     if (nb <= 0) return IREC_OK;
+    if (max_aux <= 0) return irec_fail(IREC_E_INVALID, "beam_decode: max_aux must be > 0");
     k_beam_decode<<<std::min(nb, 8 * irec_device().sm_count), 256, 0, (cudaStream_t)stream>>>(
         p_loc, p_scale, gather_idx, block_offsets, nb, seed, indices, max_aux, n_aux, irec_device().d_T,
-        irec_ratio_tab(), out_sample);
+        irec_ratio_tab(), irec_ratio_len(), out_sample, out_status);
     irec_count_launch();
     return irec_check_launch("k_beam_decode");
 }

@@ -135,6 +135,13 @@ int irec_set_thread_aux_ratios(const float* dev_ratios, int n)
     return IREC_OK;
 }
 
+int irec_aux_ratio_len(void)
+{
+    if (tl_ratio) return tl_ratio_len;
+    if (irec_init() != IREC_OK) return 0;
+    return irec_device().ratio_len;
+}
+
 float irec_aux_ratio(int i)
 {
     // rec/coding/coder.py:16,218-220: np.power(i + 1., -0.7864636765648174) (float64), cast to float32

@@ -20,6 +20,8 @@ __device__ double2 g_bm_sc[257];
 #include "irec_beam.cuh"
 #include "irec_host.h"
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 // per-lane chunk sum: 32 dims starting at chunk's first dim; A4/M4 in CI layout (q0 = first quad index)
 __device__ __forceinline__ float is_score_chunk(const float4* __restrict__ A4, const float4* __restrict__ M4, int P, int q0,
@@ -187,11 +189,25 @@ __global__ void k_is_normal_stream(TfStream st, int64_t start, int64_t n, float*
 }
 
 // ---------------------------------------------------------------------------------------------
-// GaussianCoder.encode_block / decode_block with an ImportanceSampler, one CTA per coder-block
-// (coder.py:493-584).  Running target/coder live in shared memory (plain layout), the per-partition
-// coefficients in CI layout.
+// GaussianCoder.encode_block with an ImportanceSampler, one CTA per coder-block (coder.py:493-559).
+// Running target/coder live in shared memory (plain layout), the per-partition coefficients in CI layout.
+//
+// Candidate table.  The candidates of partition k are z[s, d] = element s*D + d of the stream seeded with
+// `seed + k` (importance_sampling.py:38,54; coder.py:523,538: the seed does not depend on the coder-block), so every
+// block of a launch with the same size D scores the SAME S x D standard normals.  k_is_ztab evaluates them ONCE per
+// launch ([size][k][s][DP] float32, rows in CI layout) and the blocks stream them from L2 -- one coalesced 16-byte load
+// per quad instead of a Philox4x32-10 group and two float64-accurate Box-Muller pairs (~100 lane-instructions per
+// candidate-dim, profiles/r1_is_block_b_ncu.md).  Sizes without a table (a third distinct block size, or a table
+// beyond IS_TAB_MAX_BYTES) fall back to generating in place; both give the same bits.
 // ---------------------------------------------------------------------------------------------
 #define IS_MAX_D 4096
+#define IS_MAX_SIZES 2
+#define IS_TAB_MAX_BYTES ((size_t)512 << 20)
+struct IsPlan {
+    int32_t n_sizes;
+    int32_t D[IS_MAX_SIZES];
+    int32_t pad;
+};
 struct IsBlockArgs {
     const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
     const int64_t* gidx; const int64_t* offs; int nb;
@@ -202,9 +218,111 @@ struct IsBlockArgs {
     int64_t* out_indices; int max_aux; int32_t* out_n_idx; int32_t* out_status; float* out_sample;
     const float* ratio_tab; int ratio_len;
     int DPmax;
+    const IsPlan* plan;             // encode: distinct block sizes with a candidate table (nullptr: none)
+    const float* ztab;              // [IS_MAX_SIZES][max_aux][S][DPmax]
 };
 
-template <bool ENCODE>
+// distinct block sizes of the launch (single CTA; plan zeroed by the host)
+__global__ void __launch_bounds__(1024) k_is_plan(const int64_t* __restrict__ offs, int nb, IsPlan* plan)
+{
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int64_t D64 = offs[b + 1] - offs[b];
+        if (D64 <= 0 || D64 > IS_MAX_D) continue;
+        const int D = (int)D64;
+        for (int k = 0; k < IS_MAX_SIZES; ++k) {
+            const int old = atomicCAS(&plan->D[k], 0, D);
+            if (old == 0 || old == D) break;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int k = 0; k < IS_MAX_SIZES; ++k) n += plan->D[k] != 0;
+        plan->n_sizes = n;
+    }
+}
+
+// one thread per (size, partition, sample, physical quad of the CI row)
+__global__ void __launch_bounds__(256) k_is_ztab(const IsPlan* __restrict__ plan, const TfStream* __restrict__ streams, int S,
+                                                 int max_aux, int DPmax, float* __restrict__ tab)
+{
+    const int nq = DPmax >> 2;
+    const int64_t per_size = (int64_t)max_aux * S * nq;
+    const int64_t total = per_size * IS_MAX_SIZES;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / per_size);
+        const int D = plan->D[k];
+        if (D == 0) continue;
+        int64_t r = i - (int64_t)k * per_size;
+        const int q = (int)(r % nq); r /= nq;
+        const int s = (int)(r % S);
+        const int t = (int)(r / S);
+        const BeamGeom g = make_geom(D);
+        if (q >= (g.DP >> 2)) continue;
+        const int slot = q / (8 * g.P), qs = q - slot * 8 * g.P;        // CI(P): quad qs of a slot = iqd * P + l
+        const int iqd = qs / g.P, l = qs - iqd * g.P;
+        const int d0 = slot * 32 * g.P + 32 * l + 4 * iqd;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d0 < D) {
+            const TfStream st = streams[t];
+            const uint64_t j0 = (uint64_t)s * (uint64_t)D + (uint64_t)d0;
+            if ((j0 & 3) == 0) {
+                z = tf_normal_group(st, j0 >> 2);
+            } else {
+                z.x = tf_normal_elem(st, j0); z.y = tf_normal_elem(st, j0 + 1);
+                z.z = tf_normal_elem(st, j0 + 2); z.w = tf_normal_elem(st, j0 + 3);
+            }
+            if (d0 + 1 >= D) z.y = 0.f;      // dims beyond D carry A = M = 0 and add exactly 0 to a score either way
+            if (d0 + 2 >= D) z.z = 0.f;
+            if (d0 + 3 >= D) z.w = 0.f;
+        }
+        reinterpret_cast<float4*>(tab)[i] = z;
+    }
+}
+
+// table version of is_score_chunk / is_score_sample: zrow = the sample's CI row
+__device__ __forceinline__ float is_score_chunk_tab(const float4* __restrict__ A4, const float4* __restrict__ M4, int P, int q0,
+                                                    const float4* __restrict__ zrow)
+{
+    float acc = 0.f;
+    float4 z[8];
+#pragma unroll
+    for (int iq = 0; iq < 8; ++iq) z[iq] = __ldg(zrow + q0 + iq * P);
+#pragma unroll
+    for (int iq = 0; iq < 8; ++iq) {
+        const float4 A = A4[q0 + iq * P], M = M4[q0 + iq * P];
+        float d, t;
+        d = __fadd_rn(z[iq].x, -M.x); t = __fmaf_rn(A.x, d, M.x); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z[iq].y, -M.y); t = __fmaf_rn(A.y, d, M.y); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z[iq].z, -M.z); t = __fmaf_rn(A.z, d, M.z); acc = __fmaf_rn(t, d, acc);
+        d = __fadd_rn(z[iq].w, -M.w); t = __fmaf_rn(A.w, d, M.w); acc = __fmaf_rn(t, d, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float is_score_sample_tab(const float4* A4, const float4* M4, const BeamGeom& g, int lg,
+                                                     const float4* __restrict__ zrow)
+{
+    if (g.nslots == 1) {
+        float acc = is_score_chunk_tab(A4, M4, g.P, lg, zrow);
+        for (int stride = 1; stride < g.P; stride <<= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, stride));
+        return acc;
+    }
+    float stack[12];
+    float acc = 0.f;
+    for (int m = 0; m < g.nslots; ++m) {
+        acc = is_score_chunk_tab(A4, M4, 32, m * 256 + lg, zrow);
+        for (int stride = 1; stride < 32; stride <<= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, stride));
+        int lvl = 0;
+        while ((m >> lvl) & 1) { acc = __fadd_rn(stack[lvl], acc); ++lvl; }
+        stack[lvl] = acc;
+    }
+    bool have = false;
+    for (int lvl = 0; lvl < 12; ++lvl)
+        if ((g.nslots >> lvl) & 1) { acc = have ? __fadd_rn(stack[lvl], acc) : stack[lvl]; have = true; }
+    return acc;
+}
+
 __global__ void __launch_bounds__(256, 3) k_is_block(const IsBlockArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,112 +341,90 @@ __global__ void __launch_bounds__(256, 3) k_is_block(const IsBlockArgs a)
         const int D = (int)(a.offs[blk + 1] - off);
         const BeamGeom g = make_geom(D);
         const int lg = lane & (g.P - 1);
+        const float* ztab_blk = nullptr;            // candidate table of this block size (if it has one)
+        if (a.ztab) {
+#pragma unroll
+            for (int k = 0; k < IS_MAX_SIZES; ++k)
+                if (a.plan->D[k] == D) ztab_blk = a.ztab + (size_t)k * a.max_aux * a.S * DPm;
+        }
         for (int i = tid; i < g.DP; i += nt) { s_A[i] = 0.f; s_M[i] = 0.f; }
         for (int d = tid; d < D; d += nt) {
             const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
             s_pl[d] = a.p_loc[gi]; s_ps[d] = a.p_scale[gi];
-            if (ENCODE) { s_tl[d] = a.t_loc[gi]; s_ts[d] = a.t_scale[gi]; }
+            s_tl[d] = a.t_loc[gi]; s_ts[d] = a.t_scale[gi];
         }
         __syncthreads();
-        int n_idx;
-        if (ENCODE) {
-            // KL and n_aux (coder.py:499-501), canonical float64 chunk/tree sum
-            for (int c = tid; c < g.nch; c += nt) {
-                double acc = 0.0;
-                const int hi = min(D, 32 * c + 32);
-                for (int d = 32 * c; d < hi; ++d) {
-                    const double sp = (double)s_ps[d];
-                    const double dl = __dsub_rn(log((double)s_ts[d]), log(sp));
-                    const double dm = __dsub_rn(__ddiv_rn((double)s_tl[d], sp), __ddiv_rn((double)s_pl[d], sp));
-                    const double k = __dsub_rn(__dadd_rn(__dmul_rn(0.5, __dmul_rn(dm, dm)), __dmul_rn(0.5, expm1(__dmul_rn(2.0, dl)))), dl);
-                    acc = __dadd_rn(acc, k);
-                }
-                s_kl[c] = acc;
-            }
-            {
-                const int Pn = next_pow2_int(g.nch);
-                __syncthreads();
-                for (int stride = 1; stride < Pn; stride <<= 1) {
-                    for (int i = tid * 2 * stride; i + stride < g.nch; i += nt * 2 * stride) s_kl[i] = __dadd_rn(s_kl[i], s_kl[i + stride]);
-                    __syncthreads();
-                }
-            }
-            const float klf = (float)s_kl[0];
-            const float q = __fdiv_rn(klf, a.omega);
-            int n_aux = (!(q == q) || isinf(q)) ? -1 : (int)ceilf(q);
-            int status = IREC_BLK_OK;
-            if (n_aux < 0) status = IREC_BLK_BAD_KL;
-            n_idx = n_aux > 1 ? n_aux : 1;
-            if (status == IREC_BLK_OK && (n_idx > a.max_aux || n_idx > a.ratio_len)) status = IREC_BLK_TOO_LONG;
-            if (tid == 0) { a.out_n_idx[blk] = n_idx; a.out_status[blk] = status; }
-            if (status != IREC_BLK_OK) continue;
-        } else {
-            n_idx = a.in_n_idx[blk];
-            if (n_idx < 1 || n_idx > a.max_aux || n_idx > a.ratio_len) continue;
+        // KL and n_aux (coder.py:499-501), canonical float64 chunk/tree sum
+        for (int c = tid; c < g.nch; c += nt) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * c + 32);
+            for (int d = 32 * c; d < hi; ++d) acc = __dadd_rn(acc, kl_dim(s_tl[d], s_ts[d], s_pl[d], s_ps[d]));
+            s_kl[c] = acc;
         }
-        const int64_t* in_idx = ENCODE ? nullptr : a.in_indices + (size_t)blk * a.max_aux;
-        int64_t* out_idx = ENCODE ? a.out_indices + (size_t)blk * a.max_aux : nullptr;
+        const float klf = (float)block_tree_sum_f64(s_kl, g.nch);
+        const int n_aux = n_aux_from_kl(klf, a.omega);
+        int status = IREC_BLK_OK;
+        if (n_aux < 0) status = IREC_BLK_BAD_KL;
+        const int n_idx = n_aux > 1 ? n_aux : 1;
+        if (status == IREC_BLK_OK && (n_idx > a.max_aux || n_idx > a.ratio_len)) status = IREC_BLK_TOO_LONG;
+        if (tid == 0) { a.out_n_idx[blk] = n_idx; a.out_status[blk] = status; }
+        if (status != IREC_BLK_OK) continue;
+        int64_t* out_idx = a.out_indices + (size_t)blk * a.max_aux;
 
         // partitions k = 0 .. n_idx-1 ; k < n_idx-1 are auxiliary variables i = n_idx-1-k, the last is final
         for (int k = 0; k < n_idx; ++k) {
             const bool final_part = (k == n_idx - 1);
             const TfStream st = a.streams[k];
+            const float* ztab_k = ztab_blk ? ztab_blk + (size_t)k * a.S * DPm : nullptr;
             // --- parameters of this partition's (target, coder) pair ---
+            const float ratio = final_part ? 0.f : a.ratio_tab[n_idx - 1 - k];
             for (int d = tid; d < D; d += nt) {
                 const float ps = s_ps[d];
                 float sv, v = 0.f;
+                float tl_e, ts_e, pl_e;
                 if (!final_part) {
-                    const float cv = __fmul_rn(ps, ps);
-                    v = __fmul_rn(a.ratio_tab[n_idx - 1 - k], cv);
+                    // get_auxiliary_coder / get_auxiliary_target (coder.py:141-154), coder loc of the auxiliary coder is 0
+                    const float cv = __fmul_rn(ps, ps), tv = __fmul_rn(s_ts[d], s_ts[d]);
+                    v = __fmul_rn(ratio, cv);
                     sv = __fsqrt_rn(v);
+                    tl_e = __fdiv_rn(__fmul_rn(__fadd_rn(s_tl[d], -s_pl[d]), v), cv);
+                    const float var = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(v, v)), __fmul_rn(cv, cv)),
+                                                __fdiv_rn(__fmul_rn(v, __fadd_rn(cv, -v)), cv));
+                    ts_e = __fsqrt_rn(var);
+                    pl_e = 0.f;
                 } else {
                     sv = ps;
+                    tl_e = s_tl[d]; ts_e = s_ts[d]; pl_e = s_pl[d];
                 }
                 s_sv[d] = sv; s_v[d] = v;
-                if (ENCODE) {
-                    float tl_e, ts_e, pl_e;
-                    if (!final_part) {
-                        // get_auxiliary_target (coder.py:147-154), coder loc of the auxiliary coder is 0
-                        const float cv = __fmul_rn(ps, ps), tv = __fmul_rn(s_ts[d], s_ts[d]);
-                        tl_e = __fdiv_rn(__fmul_rn(__fadd_rn(s_tl[d], -s_pl[d]), v), cv);
-                        const float var = __fadd_rn(__fdiv_rn(__fmul_rn(tv, __fmul_rn(v, v)), __fmul_rn(cv, cv)),
-                                                    __fdiv_rn(__fmul_rn(v, __fadd_rn(cv, -v)), cv));
-                        ts_e = __fsqrt_rn(var);
-                        pl_e = 0.f;
-                    } else {
-                        tl_e = s_tl[d]; ts_e = s_ts[d]; pl_e = s_pl[d];
-                    }
-                    float A, M;
-                    is_coeffs(tl_e, ts_e, pl_e, sv, A, M);
-                    const int ci = ci_index(d, g.P);
-                    s_A[ci] = A; s_M[ci] = M;
-                }
+                float A, M;
+                is_coeffs(tl_e, ts_e, pl_e, sv, A, M);
+                const int ci = ci_index(d, g.P);
+                s_A[ci] = A; s_M[ci] = M;
             }
             __syncthreads();
-            // --- choose the index ---
-            int64_t idx;
-            if (ENCODE) {
-                const float4* A4 = reinterpret_cast<const float4*>(s_A);
-                const float4* M4 = reinterpret_cast<const float4*>(s_M);
-                const int64_t nsg = (a.S + g.SPW - 1) / g.SPW;
-                float bv = IS_NEG_INF;
-                int64_t bs = IS_NO_SAMPLE;
-                for (int64_t sg = warp; sg < nsg; sg += nw) {
-                    const int64_t s = sg * g.SPW + lane / g.P;
-                    const bool valid = s < a.S;
-                    float v = is_score_sample(A4, M4, g, lg, st, (uint64_t)(valid ? s : 0));
-                    v = (v == v) ? v : IS_NEG_INF;
-                    if (valid && cand_better(v, s, bv, bs)) { bv = v; bs = s; }
-                }
-                block_argbest(bv, bs, s_bv, s_bs);
-                idx = (bs == IS_NO_SAMPLE) ? 0 : bs;
-                if (tid == 0) out_idx[k] = idx;
-            } else {
-                idx = in_idx[k];
+            // --- choose the index: arg max of the importance weights (importance_sampling.py:60-72, alpha = inf) ---
+            const float4* A4 = reinterpret_cast<const float4*>(s_A);
+            const float4* M4 = reinterpret_cast<const float4*>(s_M);
+            const int64_t nsg = (a.S + g.SPW - 1) / g.SPW;
+            float bv = IS_NEG_INF;
+            int64_t bs = IS_NO_SAMPLE;
+            for (int64_t sg = warp; sg < nsg; sg += nw) {
+                const int64_t s = sg * g.SPW + lane / g.P;
+                const bool valid = s < a.S;
+                const int64_t sc = valid ? s : 0;
+                float v = ztab_k ? is_score_sample_tab(A4, M4, g, lg, reinterpret_cast<const float4*>(ztab_k + (size_t)sc * DPm))
+                                 : is_score_sample(A4, M4, g, lg, st, (uint64_t)sc);
+                v = (v == v) ? v : IS_NEG_INF;
+                if (valid && cand_better(v, s, bv, bs)) { bv = v; bs = s; }
             }
+            block_argbest(bv, bs, s_bv, s_bs);
+            const int64_t idx = (bs == IS_NO_SAMPLE) ? 0 : bs;
+            if (tid == 0) out_idx[k] = idx;
             // --- sample of this partition and conditioning (coder.py:157-171, 533-540) ---
+            const float* zrow = ztab_k ? ztab_k + (size_t)idx * DPm : nullptr;
             for (int d = tid; d < D; d += nt) {
-                const float z = tf_normal_elem(st, (uint64_t)idx * (uint64_t)D + (uint64_t)d);
+                const float z = zrow ? __ldg(zrow + ci_index(d, g.P)) : tf_normal_elem(st, (uint64_t)idx * (uint64_t)D + (uint64_t)d);
                 if (final_part) {
                     const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
                     a.out_sample[gi] = __fadd_rn(__fmul_rn(s_ps[d], z), s_pl[d]);
@@ -336,18 +432,16 @@ __global__ void __launch_bounds__(256, 3) k_is_block(const IsBlockArgs a)
                     const float av = __fadd_rn(__fmul_rn(s_sv[d], z), 0.f);
                     const float ps = s_ps[d], pl = s_pl[d], v = s_v[d];
                     const float cv = __fmul_rn(ps, ps);
-                    if (ENCODE) {
-                        const float tl = s_tl[d], ts = s_ts[d];
-                        const float tv = __fmul_rn(ts, ts);
-                        const float cmv = __fadd_rn(cv, -v);
-                        const float num = __fadd_rn(__fmul_rn(__fmul_rn(av, tv), cv),
-                                                    __fmul_rn(__fmul_rn(__fadd_rn(tl, -pl), cmv), cv));
-                        const float den = __fadd_rn(__fmul_rn(tv, v), __fmul_rn(cv, cmv));
-                        s_tl[d] = __fadd_rn(pl, __fdiv_rn(num, den));
-                        const float nvar = __fdiv_rn(__fmul_rn(__fmul_rn(tv, cv), cmv),
-                                                     __fadd_rn(__fmul_rn(v, tv), __fmul_rn(cv, cmv)));
-                        s_ts[d] = __fsqrt_rn(nvar);
-                    }
+                    const float tl = s_tl[d], ts = s_ts[d];
+                    const float tv = __fmul_rn(ts, ts);
+                    const float cmv = __fadd_rn(cv, -v);
+                    const float num = __fadd_rn(__fmul_rn(__fmul_rn(av, tv), cv),
+                                                __fmul_rn(__fmul_rn(__fadd_rn(tl, -pl), cmv), cv));
+                    const float den = __fadd_rn(__fmul_rn(tv, v), __fmul_rn(cv, cmv));
+                    s_tl[d] = __fadd_rn(pl, __fdiv_rn(num, den));
+                    const float nvar = __fdiv_rn(__fmul_rn(__fmul_rn(tv, cv), cmv),
+                                                 __fadd_rn(__fmul_rn(v, tv), __fmul_rn(cv, cmv)));
+                    s_ts[d] = __fsqrt_rn(nvar);
                     s_pl[d] = __fadd_rn(pl, av);
                     s_ps[d] = __fsqrt_rn(__fadd_rn(cv, -v));
                 }
@@ -357,10 +451,94 @@ __global__ void __launch_bounds__(256, 3) k_is_block(const IsBlockArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GaussianCoder.decode_block with an ImportanceSampler (coder.py:561-584): replay of the chosen candidates.
+// Every thread owns quads of dims and carries their running coder (loc, scale) through all partitions in
+// registers -- O(n_idx * D) per block, no barrier, one Philox group + two Box-Muller pairs per quad and
+// partition (k_is_block<false>, which this replaces, regenerated every element on its own: 4x the Philox
+// work, and one CTA barrier per partition).  Blocks whose index count is out of range (< 1, > max_aux,
+// > the ratio table: the reference raises IndexError / CodingError there) are filled with NaN and flagged.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_is_decode(const IsBlockArgs a)
+{
+    for (int blk = blockIdx.x; blk < a.nb; blk += gridDim.x) {
+        const int64_t off = a.offs[blk];
+        const int D = (int)(a.offs[blk + 1] - off);
+        const int n_idx = a.in_n_idx[blk];
+        const bool bad = n_idx < 1 || n_idx > a.max_aux || n_idx > a.ratio_len;
+        if (threadIdx.x == 0 && a.out_status) a.out_status[blk] = bad ? IREC_BLK_TOO_LONG : IREC_BLK_OK;
+        const int64_t* in_idx = a.in_indices + (size_t)blk * a.max_aux;
+        const int nq = (D + 3) >> 2;
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const int d0 = 4 * q;
+            float ps[4], pl[4];
+            int64_t gi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = min(d0 + e, D - 1);
+                gi[e] = a.gidx ? a.gidx[off + d] : off + d;
+                ps[e] = a.p_scale[gi[e]]; pl[e] = a.p_loc[gi[e]];
+            }
+            if (bad) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (d0 + e < D) a.out_sample[gi[e]] = __int_as_float(0x7fc00000);
+                continue;
+            }
+            for (int k = 0; k < n_idx; ++k) {
+                const TfStream st = a.streams[k];
+                const uint64_t j0 = (uint64_t)in_idx[k] * (uint64_t)D + (uint64_t)d0;
+                float z[4];
+                if ((j0 & 3) == 0) {
+                    const float4 zz = tf_normal_group(st, j0 >> 2);
+                    z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) z[e] = tf_normal_elem(st, j0 + e);
+                }
+                if (k == n_idx - 1) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (d0 + e < D) a.out_sample[gi[e]] = __fadd_rn(__fmul_rn(ps[e], z[e]), pl[e]);
+                } else {
+                    const float ratio = a.ratio_tab[n_idx - 1 - k];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {       // auxiliary sample and conditioning of the coder (coder.py:157-171, 575-580)
+                        const float cv = __fmul_rn(ps[e], ps[e]);
+                        const float v = __fmul_rn(ratio, cv);
+                        const float av = __fadd_rn(__fmul_rn(__fsqrt_rn(v), z[e]), 0.f);
+                        pl[e] = __fadd_rn(pl[e], av);
+                        ps[e] = __fsqrt_rn(__fadd_rn(cv, -v));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
-static TfStream is_stream_for_seed(int64_t seed) { return tf_stream_seeded(seed, irec_tf_op_seed(seed)); }
+// tf.random.set_seed(seed) followed by an unseeded op: the op seed is random.Random(seed).randint(0, 2**31-1) (a Mersenne
+// twister initialisation per seed) -- memoised, a coder asks for the same seed + k sequence on every call
+static TfStream is_stream_for_seed(int64_t seed)
+{
+    static std::mutex mu;
+    static std::unordered_map<int64_t, int64_t> memo;
+    int64_t op;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = memo.find(seed);
+        if (it != memo.end()) {
+            op = it->second;
+        } else {
+            op = irec_tf_op_seed(seed);
+            if (memo.size() > (1u << 20)) memo.clear();
+            memo.emplace(seed, op);
+        }
+    }
+    return tf_stream_seeded(seed, op);
+}
 
 // ---- Box-Muller tables (irec_boxmuller.cuh): built in long double on the host, one upload per device ----
 static double2 h_bm_logA[128], h_bm_logB[128], h_bm_sc[257];
@@ -505,36 +683,32 @@ int irec_is_decode_sample(const float* p_loc, const float* p_scale, int D, const
 
 size_t irec_is_block_workspace_bytes(int max_aux) { return sizeof(TfStream) * (size_t)std::max(max_aux, 1) + 256; }
 
-static int is_block_common(bool encode, IsBlockArgs& a, int64_t max_block_dim, int max_aux, int64_t seed, void* workspace,
-                           size_t workspace_bytes, cudaStream_t s)
+// candidate table of an encode launch: [IS_MAX_SIZES][max_aux][S][DP] float32, or 0 when it would be too large
+static size_t is_ztab_bytes(int64_t max_block_dim, int64_t S, int max_aux)
 {
-    if (max_block_dim <= 0 || max_block_dim > IS_MAX_D)
-        return irec_fail(IREC_E_CAPACITY, "importance-sampler blocks support at most 4096 dims per block (use block_size)");
-    if (max_aux <= 0) return irec_fail(IREC_E_INVALID, "is block: max_aux must be > 0");
-    if (workspace_bytes < irec_is_block_workspace_bytes(max_aux)) return irec_fail(IREC_E_CAPACITY, "is block: workspace too small");
+    if (max_block_dim <= 0 || max_block_dim > IS_MAX_D || S <= 0 || max_aux <= 0) return 0;
+    const char* e = getenv("IREC_IS_NO_TABLE");       // tests / A-B runs: candidates generated in place
+    if (e && e[0] == '1') return 0;
+    const BeamGeom g = make_geom((int)max_block_dim);
+    const double b = (double)sizeof(float) * IS_MAX_SIZES * (double)max_aux * (double)S * (double)g.DP;
+    return b <= (double)IS_TAB_MAX_BYTES ? (size_t)b : 0;
+}
+// workspace of irec_is_encode: stream table | IsPlan | candidate table
+size_t irec_is_encode_workspace_bytes(int nb, int64_t max_block_dim, int64_t S, int max_aux)
+{
+    (void)nb;
+    return irec_is_block_workspace_bytes(max_aux) + 256 + is_ztab_bytes(max_block_dim, S, max_aux);
+}
+
+static int is_upload_streams(int max_aux, int64_t seed, void* workspace, cudaStream_t s)
+{
     std::vector<TfStream> streams((size_t)max_aux);
     for (int k = 0; k < max_aux; ++k) streams[k] = is_stream_for_seed(seed + k);
+    // pageable source: cudaMemcpyAsync returns once the buffer has been staged, so `streams` may go out of scope and the
+    // copy is ordered before the kernels on `s` -- no host synchronisation
     if (cudaMemcpyAsync(workspace, streams.data(), sizeof(TfStream) * (size_t)max_aux, cudaMemcpyHostToDevice, s) != cudaSuccess)
         return irec_fail(IREC_E_CUDA, "is block: stream table upload failed");
-    if (cudaStreamSynchronize(s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "is block: sync failed");
-    a.streams = reinterpret_cast<const TfStream*>(workspace);
-    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
-    const BeamGeom g = make_geom((int)max_block_dim);
-    a.DPmax = g.DP;
-    const size_t smem = sizeof(float) * 8 * (size_t)g.DP;
-    // 3 CTAs of 8 warps per SM (launch bounds): the per-sample Philox -> Box-Muller -> fma chain is latency-bound
-    const int grid = std::min(a.nb, irec_device().sm_count * (smem * 3 <= (size_t)200 * 1024 ? 3 : 2));
-    if (encode) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_is_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
-        k_is_block<true><<<grid, 256, smem, s>>>(a);
-    } else {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_is_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
-        k_is_block<false><<<grid, 256, smem, s>>>(a);
-    }
-    irec_count_launch();
-    return irec_check_launch("k_is_block");
+    return IREC_OK;
 }
 
 int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
@@ -547,25 +721,70 @@ int irec_is_encode(const float* t_loc, const float* t_scale, const float* p_loc,
     IREC_ENSURE_BM();
     if (nb <= 0) return IREC_OK;
     if (S <= 0 || !(omega > 0.f)) return irec_fail(IREC_E_INVALID, "is_encode: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (max_block_dim <= 0 || max_block_dim > IS_MAX_D)
+        return irec_fail(IREC_E_CAPACITY, "importance-sampler blocks support at most 4096 dims per block (use block_size)");
+    if (max_aux <= 0) return irec_fail(IREC_E_INVALID, "is_encode: max_aux must be > 0");
+    if (workspace_bytes < irec_is_block_workspace_bytes(max_aux)) return irec_fail(IREC_E_CAPACITY, "is_encode: workspace too small");
     IsBlockArgs a{};
     a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale; a.gidx = gather_idx; a.offs = block_offsets;
     a.nb = nb; a.omega = omega; a.S = S; a.seed = seed; a.out_indices = out_indices; a.max_aux = max_aux;
     a.out_n_idx = out_n_idx; a.out_status = out_status; a.out_sample = out_sample;
-    return is_block_common(true, a, max_block_dim, max_aux, seed, workspace, workspace_bytes, (cudaStream_t)stream);
+    const int rc = is_upload_streams(max_aux, seed, workspace, s);
+    if (rc != IREC_OK) return rc;
+    a.streams = reinterpret_cast<const TfStream*>(workspace);
+    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
+    const BeamGeom g = make_geom((int)max_block_dim);
+    a.DPmax = g.DP;
+    // candidate table, when the caller's workspace has room for it (irec_is_encode_workspace_bytes)
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    const size_t head = irec_is_block_workspace_bytes(max_aux);
+    const size_t tab_bytes = is_ztab_bytes(max_block_dim, S, max_aux);
+    if (tab_bytes && workspace_bytes >= head + 256 + tab_bytes) {
+        IsPlan* dplan = reinterpret_cast<IsPlan*>(w + head);
+        float* tab = reinterpret_cast<float*>(w + head + 256);
+        if (cudaMemsetAsync(dplan, 0, sizeof(IsPlan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "is_encode: memset failed");
+        k_is_plan<<<1, 1024, 0, s>>>(block_offsets, nb, dplan);
+        irec_count_launch();
+        const int64_t items = (int64_t)IS_MAX_SIZES * max_aux * S * (g.DP >> 2);
+        const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)irec_device().sm_count * 16);
+        k_is_ztab<<<grid, 256, 0, s>>>(dplan, a.streams, (int)S, max_aux, g.DP, tab);
+        irec_count_launch();
+        a.plan = dplan; a.ztab = tab;
+    }
+    const size_t smem = sizeof(float) * 8 * (size_t)g.DP;
+    // 3 CTAs of 8 warps per SM (launch bounds)
+    const int grid = std::min(a.nb, irec_device().sm_count * (smem * 3 <= (size_t)200 * 1024 ? 3 : 2));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_is_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * IS_MAX_D)); attr = true; }
+    k_is_block<<<grid, 256, smem, s>>>(a);
+    irec_count_launch();
+    return irec_check_launch("k_is_block");
 }
 
 int irec_is_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,
                    const int64_t* block_offsets, int nb, int64_t max_block_dim, int64_t seed,
                    const int64_t* indices, int max_aux, const int32_t* n_idx,
-                   float* out_sample, void* workspace, size_t workspace_bytes, void* stream)
+                   float* out_sample, int32_t* out_status, void* workspace, size_t workspace_bytes, void* stream)
 {
     IREC_ENSURE_INIT();
     IREC_ENSURE_BM();
     if (nb <= 0) return IREC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (max_block_dim <= 0) return irec_fail(IREC_E_INVALID, "is_decode: bad sizes");
+    if (max_aux <= 0) return irec_fail(IREC_E_INVALID, "is_decode: max_aux must be > 0");
+    if (workspace_bytes < irec_is_block_workspace_bytes(max_aux)) return irec_fail(IREC_E_CAPACITY, "is_decode: workspace too small");
     IsBlockArgs a{};
     a.p_loc = p_loc; a.p_scale = p_scale; a.gidx = gather_idx; a.offs = block_offsets; a.nb = nb;
     a.seed = seed; a.in_indices = indices; a.in_n_idx = n_idx; a.max_aux = max_aux; a.out_sample = out_sample;
-    return is_block_common(false, a, max_block_dim, max_aux, seed, workspace, workspace_bytes, (cudaStream_t)stream);
+    a.out_status = out_status;
+    const int rc = is_upload_streams(max_aux, seed, workspace, s);
+    if (rc != IREC_OK) return rc;
+    a.streams = reinterpret_cast<const TfStream*>(workspace);
+    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
+    k_is_decode<<<std::min(a.nb, irec_device().sm_count * 8), 256, 0, s>>>(a);
+    irec_count_launch();
+    return irec_check_launch("k_is_decode");
 }
 
 }  // extern "C"

@@ -69,119 +69,212 @@ class BeamEncodeResult:
         self.indices, self.n_aux, self.sample, self.kl = indices, n_aux, sample, kl
 
 
+# Row capacity (`max_aux`) of a launch when the caller has not promised one: the last need seen for the same coder
+# parameters, with head-room.  The kernels compute KL and n_aux themselves and flag rows that do not fit
+# (IREC_BLK_TOO_LONG); only then the launch is repeated with the exact capacity -- no sizing pre-pass, no
+# device->host read before the launch.
+_AUX_HINT_FIRST = 128
+_aux_hint = {}
+
+
+def _hint_get(key):
+    return _aux_hint.get(key, _AUX_HINT_FIRST)
+
+
+def _hint_update(key, seen_max):
+    want = max(_AUX_HINT_FIRST, (int(seen_max * 1.25) + 63) // 64 * 64)
+    cur = _aux_hint.get(key)
+    if cur is None or want > cur or want < cur // 2:
+        _aux_hint[key] = want
+
+
+def _too_long_need(status, n_aux, max_aux, what):
+    """capacity a repeat launch needs, or None when every row fitted; rows flagged although they would fit the
+    capacity exceed the auxiliary-ratio table in force (learned ratios) -- the reference's CodingError"""
+    import numpy as np
+    st = status.numpy() if hasattr(status, "numpy") else np.asarray(status)
+    na = n_aux.numpy() if hasattr(n_aux, "numpy") else np.asarray(n_aux)
+    long_rows = st == N.BLK_TOO_LONG
+    if not long_rows.any():
+        return None
+    need = int(na[long_rows].max())
+    ratio_len = int(N.load_library().irec_aux_ratio_len())
+    if need > ratio_len or need <= max_aux:
+        b = int(np.flatnonzero(long_rows)[0])
+        raise CodingError(f"{what}: block {b}: KL divergence higher than auxiliary variables can account for "
+                          f"(needs {int(na[b])}, the ratio table covers {ratio_len})")
+    return need
+
+
 class PendingBeamResult:
     """Result of a launched beam encode whose index lists have not been read back yet: the packed (status, n_aux, indices)
     rows are on their way to pinned host memory; `indices()` waits for that copy only (not for later work on the stream),
     checks the per-block status and builds the Python lists.  Lets a caller that codes several tensors in a row (the
-    levels of a model, a batch of images) overlap the host-side list building of one launch with the next launch."""
-    __slots__ = ("_host", "_event", "_nb", "sample", "kl", "_lists")
+    levels of a model, a batch of images) overlap the host-side list building of one launch with the next launch.
+    Without a promised `max_aux` a row may not have fitted the guessed capacity: `indices()` then repeats the launch
+    (same output tensors, `retried` = True) -- `sample` is final only once `indices()` has returned."""
+    __slots__ = ("_host", "_event", "_nb", "sample", "kl", "_lists", "_retry", "_max_aux", "_hint_key", "retried")
 
-    def __init__(self, host, event, nb, sample, kl):
+    def __init__(self, host, event, nb, sample, kl, retry=None, max_aux=0, hint_key=None):
         self._host, self._event, self._nb, self.sample, self.kl, self._lists = host, event, nb, sample, kl, None
+        self._retry, self._max_aux, self._hint_key, self.retried = retry, max_aux, hint_key, False
 
     def indices(self):
         if self._lists is None:
             self._event.synchronize()
             packed = self._host
-            status, n_aux, idx = packed[:, 0], packed[:, 1], packed[:, 2:]
+            status, n_aux = packed[:, 0], packed[:, 1]
+            if self._retry is not None:
+                need = _too_long_need(status, n_aux, self._max_aux, "beam encode")
+                if need is not None:
+                    packed = self._retry(need)
+                    status, n_aux = packed[:, 0], packed[:, 1]
+                    self.retried = True
+                if self._hint_key is not None and packed.shape[0]:
+                    _hint_update(self._hint_key, int(n_aux.max()))
             _raise_status(status, n_aux, "beam encode")
-            idx_np, na_np = idx.numpy(), n_aux.numpy().tolist()
+            idx_np, na_np = packed[:, 2:].numpy(), n_aux.numpy().tolist()
             self._lists = [idx_np[b, :na_np[b]].tolist() for b in range(self._nb)]
-            self._host = None
+            self._host = self._retry = None
         return self._lists
 
 
 def beam_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, max_block_dim, omega, S, B, seed,
                        max_aux=None, return_device=False, lazy=False):
-    """BeamSearchCoder.encode_block over nb blocks in one launch (beam_search_coder.py:53-122)."""
+    """BeamSearchCoder.encode_block over nb blocks in one launch (beam_search_coder.py:53-122).  max_aux: promised row
+    capacity (no block needs more auxiliary variables); None = guessed from earlier calls and grown on demand."""
     lib = N.lib()
     dev = t_loc.device
-    kl = None
-    if max_aux is None:
-        kl, na = kl_naux(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega)
-        na_h = na.cpu()
-        if bool((na_h <= 0).any()):
-            b = int((na_h <= 0).nonzero()[0])
-            raise CodingError(f"beam encode: block {b}: KL divergence is not finite or zero (n_aux={int(na_h[b])})")
-        max_aux = int(na_h.max())
-    ws_bytes = int(lib.irec_beam_encode_workspace_bytes(nb, int(max_block_dim), int(S), int(B), int(max_aux)))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    out_idx = torch.empty((nb, max_aux), dtype=torch.int32, device=dev)
-    out_na = torch.empty(nb, dtype=torch.int32, device=dev)
-    out_st = torch.empty(nb, dtype=torch.int32, device=dev)
+    promised = max_aux is not None
+    hint_key = (str(dev), float(omega))
+    if not promised:
+        max_aux = _hint_get(hint_key)
     out_sample = torch.empty_like(t_loc)
-    N.check(lib.irec_beam_encode(N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx),
-                                 N.ptr(block_offsets), nb, int(max_block_dim), float(omega), int(S), int(B), int(seed),
-                                 N.ptr(out_idx), int(max_aux), N.ptr(out_na), N.ptr(out_st), N.ptr(out_sample),
-                                 N.ptr(ws), ws_bytes, N.stream_ptr()), "irec_beam_encode")
+
+    def launch(cap):
+        ws_bytes = int(lib.irec_beam_encode_workspace_bytes(nb, int(max_block_dim), int(S), int(B), int(cap)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out_idx = torch.empty((nb, cap), dtype=torch.int32, device=dev)
+        out_na = torch.empty(nb, dtype=torch.int32, device=dev)
+        out_st = torch.empty(nb, dtype=torch.int32, device=dev)
+        N.check(lib.irec_beam_encode(N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx),
+                                     N.ptr(block_offsets), nb, int(max_block_dim), float(omega), int(S), int(B), int(seed),
+                                     N.ptr(out_idx), int(cap), N.ptr(out_na), N.ptr(out_st), N.ptr(out_sample),
+                                     N.ptr(ws), ws_bytes, N.stream_ptr()), "irec_beam_encode")
+        return out_idx, out_na, out_st
+
+    def pack(outs):
+        out_idx, out_na, out_st = outs
+        return torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1)
+
+    outs = launch(int(max_aux))
     if return_device:
-        return BeamEncodeResult(out_idx, out_na, out_sample, kl), out_st
+        return BeamEncodeResult(outs[0], outs[1], out_sample, None), outs[2]
     if lazy:
-        packed_dev = torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1)
+        packed_dev = pack(outs)
         host = torch.empty(packed_dev.shape, dtype=packed_dev.dtype, pin_memory=True)
         host.copy_(packed_dev, non_blocking=True)
         event = torch.cuda.Event()
         event.record()
-        return PendingBeamResult(host, event, nb, out_sample, kl)
-    packed = torch.cat([out_st.view(-1, 1), out_na.view(-1, 1), out_idx], dim=1).cpu()   # one D2H copy
+        retry = None if promised else (lambda need: pack(launch(need)).cpu())
+        return PendingBeamResult(host, event, nb, out_sample, None, retry=retry, max_aux=int(max_aux),
+                                 hint_key=None if promised else hint_key)
+    packed = pack(outs).cpu()                                          # one D2H copy
+    if not promised:
+        need = _too_long_need(packed[:, 0], packed[:, 1], int(max_aux), "beam encode")
+        if need is not None:
+            packed = pack(launch(need)).cpu()
+        if nb:
+            _hint_update(hint_key, int(packed[:, 1].max()))
     status, n_aux, idx = packed[:, 0], packed[:, 1], packed[:, 2:]
     _raise_status(status, n_aux, "beam encode")
     idx_np, na_np = idx.numpy(), n_aux.numpy().tolist()          # numpy slicing: ~10x cheaper per block than tensor indexing
     indices = [idx_np[b, :na_np[b]].tolist() for b in range(nb)]
-    return BeamEncodeResult(indices, n_aux, out_sample, kl)
+    return BeamEncodeResult(indices, n_aux, out_sample, None)
 
 
 def pack_indices(indices, dtype, device):
-    nb = len(indices)
-    max_aux = max(1, max(len(i) for i in indices))
+    """per-block index lists -> ([nb, max_aux] tensor, [nb] counts, max_aux) with ONE host->device copy (counts in the
+    first column of the staging array)"""
     import numpy as np
+    nb = len(indices)
+    lens = [len(i) for i in indices]
+    max_aux = max(1, max(lens) if lens else 1)
     np_dtype = np.int64 if dtype == torch.int64 else np.int32
-    host = np.zeros((nb, max_aux), dtype=np_dtype)
-    n = np.zeros(nb, dtype=np.int32)
+    host = np.zeros((nb, max_aux + 1), dtype=np_dtype)
     for b, ind in enumerate(indices):
-        k = len(ind)
-        n[b] = k
+        k = lens[b]
+        host[b, 0] = k
         if k:
-            host[b, :k] = np.asarray([int(v) for v in ind], dtype=np_dtype)
-    return torch.from_numpy(host).to(device), torch.from_numpy(n).to(device), max_aux
+            host[b, 1:k + 1] = np.asarray(ind, dtype=np_dtype) if not isinstance(ind, np.ndarray) else ind.astype(np_dtype, copy=False)
+    both = torch.from_numpy(host).to(device)
+    idx = both[:, 1:].contiguous()
+    n = both[:, 0].to(torch.int32).contiguous()
+    return idx, n, max_aux
 
 
-def beam_decode_blocks(p_loc, p_scale, gather_idx, block_offsets, nb, S, seed, indices):
+def _check_index_counts(indices, what):
+    """host-side validation of per-block index lists before a decode launch (no device read): the reference raises
+    CodingError for a list longer than the ratio table (coder.py:226-231)"""
+    longest = max((len(i) for i in indices), default=0)
+    ratio_len = int(N.load_library().irec_aux_ratio_len())
+    if longest > ratio_len:
+        raise CodingError(f"{what}: KL divergence higher than auxiliary variables can account for. Maximum possible number "
+                          f"of partitions is {ratio_len}. Requested {longest}")
+
+
+def beam_decode_blocks(p_loc, p_scale, gather_idx, block_offsets, nb, S, seed, indices, return_status=False):
     """BeamSearchCoder.decode_block over nb blocks (beam_search_coder.py:124-148); `indices` is a list
-    of per-block index lists in partition order, or a tuple (idx_tensor, n_aux_tensor, max_aux)."""
+    of per-block index lists in partition order, or a tuple (idx_tensor, n_aux_tensor, max_aux) of device tensors
+    (then pass return_status=True to receive the per-block status tensor: rows the kernel refused decode to NaN)."""
     lib = N.lib()
     dev = p_loc.device
     if isinstance(indices, tuple):
         idx, n_aux, max_aux = indices
     else:
+        _check_index_counts(indices, "beam decode")
         idx, n_aux, max_aux = pack_indices(indices, torch.int32, dev)
     out = torch.empty_like(p_loc)
+    status = torch.empty(nb, dtype=torch.int32, device=dev) if return_status else None
     N.check(lib.irec_beam_decode(N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx), N.ptr(block_offsets), nb, int(S),
-                                 int(seed), N.ptr(idx), int(max_aux), N.ptr(n_aux), N.ptr(out), N.stream_ptr()),
-            "irec_beam_decode")
-    return out
+                                 int(seed), N.ptr(idx), int(max_aux), N.ptr(n_aux), N.ptr(out), N.ptr(status),
+                                 N.stream_ptr()), "irec_beam_decode")
+    return (out, status) if return_status else out
 
 
-def is_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, max_block_dim, omega, S, seed):
-    """GaussianCoder.encode_block with an ImportanceSampler over nb blocks (coder.py:493-559)."""
+def is_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, max_block_dim, omega, S, seed, max_aux=None):
+    """GaussianCoder.encode_block with an ImportanceSampler over nb blocks (coder.py:493-559).  The kernel computes KL and
+    the number of auxiliary variables itself; results come back in ONE device->host copy."""
     lib = N.lib()
     dev = t_loc.device
-    _, na = kl_naux(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega)
-    na_h = na.cpu()
-    if bool((na_h < 0).any()):
-        raise CodingError("importance encode: KL divergence is not finite")
-    max_aux = max(1, int(na_h.max()))
-    ws_bytes = int(lib.irec_is_block_workspace_bytes(max_aux))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    out_idx = torch.empty((nb, max_aux), dtype=torch.int64, device=dev)
-    out_n = torch.empty(nb, dtype=torch.int32, device=dev)
-    out_st = torch.empty(nb, dtype=torch.int32, device=dev)
+    promised = max_aux is not None
+    hint_key = (str(dev), float(omega), "is")
+    if not promised:
+        max_aux = _hint_get(hint_key)
     out_sample = torch.empty_like(t_loc)
-    N.check(lib.irec_is_encode(N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx),
-                               N.ptr(block_offsets), nb, int(max_block_dim), float(omega), int(S), int(seed),
-                               N.ptr(out_idx), max_aux, N.ptr(out_n), N.ptr(out_st), N.ptr(out_sample), N.ptr(ws),
-                               ws_bytes, N.stream_ptr()), "irec_is_encode")
-    st_h, n_h, idx_h = out_st.cpu(), out_n.cpu(), out_idx.cpu()
+
+    def launch(cap):
+        ws_bytes = int(lib.irec_is_encode_workspace_bytes(nb, int(max_block_dim), int(S), int(cap)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out_idx = torch.empty((nb, cap), dtype=torch.int64, device=dev)
+        out_n = torch.empty(nb, dtype=torch.int32, device=dev)
+        out_st = torch.empty(nb, dtype=torch.int32, device=dev)
+        N.check(lib.irec_is_encode(N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx),
+                                   N.ptr(block_offsets), nb, int(max_block_dim), float(omega), int(S), int(seed),
+                                   N.ptr(out_idx), cap, N.ptr(out_n), N.ptr(out_st), N.ptr(out_sample), N.ptr(ws),
+                                   ws_bytes, N.stream_ptr()), "irec_is_encode")
+        return torch.cat([out_st.view(-1, 1).to(torch.int64), out_n.view(-1, 1).to(torch.int64), out_idx], dim=1).cpu()
+
+    packed = launch(int(max_aux))
+    if not promised:
+        need = _too_long_need(packed[:, 0], packed[:, 1], int(max_aux), "importance encode")
+        if need is not None:
+            packed = launch(need)
+        if nb:
+            _hint_update(hint_key, int(packed[:, 1].max()))
+    st_h, n_h, idx_h = packed[:, 0], packed[:, 1], packed[:, 2:]
+    if bool((st_h == N.BLK_BAD_KL).any()):
+        raise CodingError("importance encode: KL divergence is not finite")
     _raise_status(st_h, n_h, "importance encode")
     idx_np, n_np = idx_h.numpy(), n_h.numpy().tolist()
     indices = [idx_np[b, :n_np[b]].tolist() for b in range(nb)]
@@ -189,14 +282,19 @@ def is_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, 
 
 
 def is_decode_blocks(p_loc, p_scale, gather_idx, block_offsets, nb, max_block_dim, seed, indices):
+    """GaussianCoder.decode_block with an ImportanceSampler over nb blocks (coder.py:561-584): one launch, O(n_aux * D) per
+    block, the index lists packed and uploaded once."""
     lib = N.lib()
     dev = p_loc.device
+    if any(len(i) < 1 for i in indices):
+        raise IndexError("importance decode: empty index list")          # reference: indices[0] on an empty list
+    _check_index_counts(indices, "importance decode")
     idx, n_idx, max_aux = pack_indices(indices, torch.int64, dev)
     ws_bytes = int(lib.irec_is_block_workspace_bytes(max_aux))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     out = torch.empty_like(p_loc)
     N.check(lib.irec_is_decode(N.ptr(p_loc), N.ptr(p_scale), N.ptr(gather_idx), N.ptr(block_offsets), nb,
-                               int(max_block_dim), int(seed), N.ptr(idx), max_aux, N.ptr(n_idx), N.ptr(out), N.ptr(ws),
+                               int(max_block_dim), int(seed), N.ptr(idx), max_aux, N.ptr(n_idx), N.ptr(out), None, N.ptr(ws),
                                ws_bytes, N.stream_ptr()), "irec_is_decode")
     return out
 

@@ -4,6 +4,7 @@ PyTorch is used only as the owner of device memory and streams: tensors are hand
 as raw device pointers (`tensor.data_ptr()`), together with the current CUDA stream.  There is no
 CPU fallback: if the shared library is missing or no CUDA device is present, calls raise.
 """
+import collections
 import ctypes as C
 import os
 
@@ -27,11 +28,13 @@ _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size
 
 _SIGNATURES = {
     "irec_version": (C.c_int, []),
+    "irec_build_hash": (C.c_char_p, []),
     "irec_last_error_string": (C.c_char_p, []),
     "irec_init": (C.c_int, []),
     "irec_get_ndtri_table": (C.c_int, [_vp]),
     "irec_aux_ratio": (C.c_float, [_i32]),
     "irec_set_thread_aux_ratios": (C.c_int, [_vp, _i32]),
+    "irec_aux_ratio_len": (C.c_int, []),
     "irec_tf_op_seed": (C.c_int64, [_i64]),
     "irec_split_permutation": (C.c_int, [_i64, _i64, _vp]),
     "irec_beam_uniform_int": (C.c_int, [_i64, _i64, _i64, _vp, _vp]),
@@ -44,7 +47,7 @@ _SIGNATURES = {
     "irec_beam_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i32, _i32, _i64,
                                    _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irec_beam_encode_path": (C.c_int, [_i32, _i64, _i32, _i32]),
-    "irec_beam_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "irec_beam_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "irec_beam_state_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "irec_beam_state_init": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i64, _vp]),
     "irec_beam_state_query": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
@@ -59,9 +62,10 @@ _SIGNATURES = {
     "irec_is_coded_sample": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "irec_is_decode_sample": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "irec_is_block_workspace_bytes": (C.c_size_t, [_i32]),
+    "irec_is_encode_workspace_bytes": (C.c_size_t, [_i32, _i64, _i64, _i32]),
     "irec_is_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i64, _i64,
                                  _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "irec_is_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "irec_is_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irec_launch_count": (C.c_int64, []),
     # include/irec_io.h -- host C++ (arithmetic coder + .rec container), no CUDA calls
     "irec_ac_encode": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
@@ -132,6 +136,9 @@ def aux_ratio(i):
     return float(load_library().irec_aux_ratio(int(i)))
 
 
+_borrowed = collections.deque()      # (event, tensor): ratio tables still referenced by enqueued kernels
+
+
 class thread_aux_ratios:
     """`with thread_aux_ratios(table):` -- learned auxiliary variance ratios (a float32 CUDA tensor, or None for the
     power law) for every libirec call made by this thread inside the block (include/irec.h: irec_set_thread_aux_ratios)."""
@@ -148,7 +155,13 @@ class thread_aux_ratios:
 
     def __exit__(self, *exc):
         if self.table is not None:
-            torch.cuda.current_stream().synchronize()      # the table is borrowed until the enqueued work has finished
+            # the table is borrowed until the enqueued work has finished: instead of synchronising the stream, keep a
+            # reference parked behind an event and drop it once the event has completed
+            ev = torch.cuda.Event()
+            ev.record()
+            _borrowed.append((ev, self.table))
+            while _borrowed and _borrowed[0][0].query():
+                _borrowed.popleft()
             check(load_library().irec_set_thread_aux_ratios(None, 0), "irec_set_thread_aux_ratios")
         return False
 

@@ -475,3 +475,81 @@ def test_exponent_table_cache_is_transparent(cuda):
     for (ri, rs), (gi, gs), (ai, as_) in zip(ref, got, again):
         assert gi == ri and torch.equal(gs, rs)
         assert ai == ri and torch.equal(as_, rs)
+
+
+# ------------------------------------------------------------------------------------------ round 2: decode validation, IS candidate table
+def test_decode_rejects_index_lists_beyond_the_ratio_table(cuda):
+    """a learned ratio table shorter than an index list must raise CodingError (reference coder.py:226-231),
+    not read past the table; the kernels flag such rows and write NaN instead of garbage."""
+    import torch
+    from irec_b200 import Normal, engine as E, native as N
+    from rec.coding import BeamSearchCoder, GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+    from rec.coding.utils import CodingError
+    tl, ts, pl, ps = synth.c2(100, data_seed=3)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    table = torch.tensor([1.0, 0.5, 0.4], dtype=torch.float32, device=cuda)
+    long_list = [1, 2, 3, 4, 5]
+    for coder in (BeamSearchCoder(kl_per_partition=3., n_beams=4), GaussianCoder(3., ImportanceSampler(coding_bits=4.))):
+        with N.thread_aux_ratios(table):
+            assert N.load_library().irec_aux_ratio_len() == 3
+            with pytest.raises(CodingError):
+                coder._decode_flat(p.loc.reshape(-1), p.scale.reshape(-1), None, *E.make_block_offsets(100, None, cuda)[:2], 100, 1,
+                                   [list(long_list)])
+        assert N.load_library().irec_aux_ratio_len() == 65536
+    # device-side check (index counts only known on the device): status + NaN
+    offs, nb, _ = E.make_block_offsets(200, 100, cuda)
+    pl2 = torch.zeros(200, device=cuda); ps2 = torch.ones(200, device=cuda)
+    idx = torch.zeros((2, 8), dtype=torch.int32, device=cuda)
+    n_aux = torch.tensor([2, 7], dtype=torch.int32, device=cuda)
+    with N.thread_aux_ratios(table):
+        out, status = E.beam_decode_blocks(pl2, ps2, None, offs, nb, 20, 1, (idx, n_aux, 8), return_status=True)
+    assert status.tolist() == [N.BLK_OK, N.BLK_TOO_LONG]
+    assert torch.isfinite(out[:100]).all() and torch.isnan(out[100:]).all()
+    with pytest.raises(IndexError):                       # reference: indices[0] of an empty list
+        E.is_decode_blocks(pl2, ps2, None, offs, nb, 100, 1, [[1], []])
+
+
+@pytest.mark.parametrize("n,bs", [(2500, 1000), (300, 128), (37, None)])
+def test_is_encode_candidate_table_equals_in_place(cuda, n, bs):
+    """the launch-wide candidate table (k_is_ztab) and in-place Philox/Box-Muller give the same indices and sample bits"""
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+    tl, ts, pl, ps = synth.c2(n, data_seed=91)
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    res = []
+    for no_table in ("0", "1"):
+        os.environ["IREC_IS_NO_TABLE"] = no_table
+        try:
+            coder = GaussianCoder(kl_per_partition=3., sampler=ImportanceSampler(coding_bits=3. / np.log(2)), block_size=bs)
+            res.append(coder.encode(t, p, seed=11))
+        finally:
+            os.environ.pop("IREC_IS_NO_TABLE", None)
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1])
+
+
+def test_encode_grows_row_capacity_without_presizing(cuda):
+    """no sizing pre-pass: a block that needs more auxiliary variables than the guessed capacity is re-launched with the
+    exact one (same result as with a promised max_aux)"""
+    import torch
+    from irec_b200 import Normal, engine as E
+    from rec.coding import BeamSearchCoder
+    tl, ts, pl, ps = synth.c2(1000, data_seed=5)
+    coder = BeamSearchCoder(kl_per_partition=1.0, n_beams=3, extra_samples=2.0)     # ~260 nats / 1 nat: > 128 variables
+    t = Normal(tl[None, :], ts[None, :], device=cuda)
+    p = Normal(pl[None, :], ps[None, :], device=cuda)
+    E._aux_hint.clear()
+    idx1, s1 = coder.encode(t, p, seed=3)
+    assert len(idx1) > E._AUX_HINT_FIRST
+    ref = O.beam_encode_block(tl, ts, pl, ps, 1.0, coder.n_samples, 3, 3)
+    assert list(idx1) == ref["indices"].tolist()
+    assert np.array_equal(bits(s1.cpu().numpy().reshape(-1)), bits(ref["sample"]))
+    idx2, s2 = coder.encode(t, p, seed=3)                 # the hint now covers it: single launch
+    assert idx2 == idx1 and torch.equal(s1, s2)
+    E._aux_hint.clear()
+    get, s3 = coder.encode_batch(t, p, seed=3, lazy=True)
+    assert get()[0] == idx1 and torch.equal(s3.reshape(-1), s1.reshape(-1))
