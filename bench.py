@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the iREC beam-search encode hot path on B200.
+"""bench.py -- throughput of the iREC encode hot path on B200 (BASELINE.json metric).
 
-Workload (BASELINE.json configs[3] shape, weak scaling): per GPU a batch of IMAGES_PER_GPU ImageNet32-shaped
-synthetic images through resnet_vae latents -- 24 latent tensors [16,16,32] per image, block_size 1000
-(9 coder-blocks per tensor), beam search n_beams=20, extra_samples=1.2 (S=36), kl_per_partition=3 nats,
-coding seed 42.  8 GPUs x 128 images = the 1024-image batch of configs[3].  One "step" = one pass of the
-encoder over the whole per-GPU batch: 24 sequential level launches (a level's prior depends on the previous
-level's sample in the real model), every launch coding 128 x 9 blocks.
+Headline workload = BASELINE.json configs[3] itself: a batch of 1024 ImageNet32-shaped synthetic images through resnet_vae
+latents -- 24 latent tensors [16,16,32] per image, block_size 1000 (9 coder-blocks per tensor), beam search n_beams=20,
+extra_samples=1.2 (S=36), kl_per_partition=3 nats, coding seed 42 -- sharded over the N ranks by images (strong scaling:
+1024 images in total whatever N; no collective in the loop).  One "step" = one pass of the encoder over the whole batch: 24
+sequential level launches (a level's prior depends on the previous level's sample in the real model), every launch coding
+(1024/N) x 9 coder-blocks.
 
-  value  : candidates scored / s, inputs resident in HBM (CUDA events)
-  e2e    : same through the public API (rec.coding.BeamSearchCoder.encode_batch) from pinned host buffers,
-           host<->device copies and index read-back inside the timed region
-  roofline: INT32/FP32 issue rate of the dominant kernel (k_beam_encode_resident2<20>), algorithmic
-           instructions per candidate-dim W = 10 + 24/B' (SURVEY.md 8d); secondary: HBM bytes and the
-           shared-memory wavefront rate (the measured limiter of the hot loop, profiles/)
+  value    : candidates scored / s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e      : same through the public API (rec.coding.BeamSearchCoder.encode_batch) from pinned host buffers,
+             host<->device copies and index read-back inside the timed region, over all --steps
+  roofline : INT32/FP32 issue rate of the dominant kernel, algorithmic instructions per candidate-dim
+             W = 10 + 24/B' (SURVEY.md 8d); secondary: HBM bytes and the shared-memory wavefront rate (profiles/)
+  c5       : BASELINE.json configs[4] -- ONE coder-block (D=64), kl_per_partition 14..20 bits (S up to 2^24 candidates per
+             auxiliary variable), the candidate index range split over the N ranks, per-rank top-B records exchanged over
+             NVLink peer memory (irec_p2p_exchange) and merged; oracle check where S is small, 1-GPU equality at S = 2^24
+  is       : the importance-sampler coder (GaussianCoder + ImportanceSampler) on 256 latents, encode + decode
+  cpu_baseline / cpu_baselines, refform : CPU legs on rank 0 at N=1 (C oracle on all host threads; the reference-structured
+             NumPy port; canonical-vs-reference-form decision statistics on a bounded sample)
 
-`--impl reference` times the CPU port of the reference (the C oracle, all host threads) on a bounded sample.
+`--impl reference` times the CPU port of the reference (the C oracle, all host threads) on a bounded sample of the same
+workload and prints the same JSON line with "impl": "reference".
 """
 import argparse
 import json
@@ -32,7 +38,7 @@ for p in (ROOT, os.path.join(ROOT, "relative-entropy-coding_b200"), os.path.join
     if p not in sys.path:
         sys.path.insert(0, p)
 
-IMAGES_PER_GPU = 128
+IMAGES_TOTAL = 1024
 LEVELS = 24
 LATENT = 8192            # 16*16*32
 BLOCK = 1000
@@ -40,6 +46,10 @@ OMEGA, EXTRA, NBEAMS, SEED = 3.0, 1.2, 20, 42
 S = int(np.exp(OMEGA * EXTRA))
 MAX_AUX = 256
 METRIC = "iREC candidates scored/sec (beam-search encode; candidate = one (sample, beam) pair scored over all dims of its coder-block)"
+C5_BITS = (14.0, 16.0, 18.0, 20.0)
+C5_DIMS, C5_MIN_AUX = 64, 8
+IS_IMAGES = 256
+W_IS = 34.0              # lane-instructions per candidate-dim of the importance sampler
 
 
 def synth_level(image, level, n=LATENT):
@@ -48,13 +58,24 @@ def synth_level(image, level, n=LATENT):
     return synth.c2(n, data_seed=1000 * image + level)
 
 
-def work_model(n_aux, dims):
+def synth_levels(images, threads):
+    """host[level] = list over images of (tl, ts, pl, ps); numpy releases the GIL in the generators"""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [(i, lvl) for lvl in range(LEVELS) for i in images]
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        res = list(ex.map(lambda j: synth_level(*j), jobs, chunksize=64))
+    n = len(images)
+    return [res[lvl * n:(lvl + 1) * n] for lvl in range(LEVELS)]
+
+
+def work_model(n_aux, dims, s=S, nbeams=NBEAMS):
     """algorithmic work of a set of blocks: candidates, candidate-dims, partitions, lane-instructions"""
     n_aux = np.asarray(n_aux, np.int64)
     dims = np.asarray(dims, np.int64)
-    cand = S * 1 + (n_aux - 1) * S * NBEAMS                 # t = 0 has one (empty) beam
+    bp = min(nbeams, s)
+    cand = s * 1 + (n_aux - 1) * s * bp                     # t = 0 has one (empty) beam
     cd = cand * dims
-    instr = dims * (S * 1 * (10 + 24 / 1) + (n_aux - 1) * S * NBEAMS * (10 + 24 / NBEAMS))
+    instr = dims * (s * 1 * (10 + 24 / 1) + (n_aux - 1) * s * bp * (10 + 24 / bp))
     return int(cand.sum()), int(cd.sum()), int(n_aux.sum()), float(instr.sum())
 
 
@@ -104,18 +125,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_sample(n_blocks, threads):
-    """oracle (C port of the reference) on `n_blocks` coder-blocks of the same workload, `threads` host threads"""
-    from concurrent.futures import ThreadPoolExecutor
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle/)
+def cpu_sample_jobs(n_blocks):
+    """`n_blocks` coder-blocks of the headline workload (full 1000-dim blocks of images 0, 1, ...)"""
     from oracle import oracle as O
-    O.lib()
-    O.ndtri_table()
     perm = O.shuffle_perm(LATENT, SEED)
     jobs = []
     for i in range(n_blocks):
         tl, ts, pl, ps = synth_level(i // 8, i % LEVELS)
         sel = perm[(i % 8) * BLOCK:(i % 8 + 1) * BLOCK]
         jobs.append((tl[sel], ts[sel], pl[sel], ps[sel]))
+    return jobs
+
+
+def cpu_port_sample(n_blocks, threads):
+    """oracle (C port of the reference) on `n_blocks` coder-blocks of the same workload, `threads` host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.lib()
+    O.ndtri_table()
+    jobs = cpu_sample_jobs(n_blocks)
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         res = list(ex.map(lambda j: O.beam_encode_block(*j, OMEGA, S, NBEAMS, SEED), jobs))
@@ -124,9 +153,36 @@ def cpu_port_sample(n_blocks, threads):
     return cand / dt, cd / dt, parts / dt, dt, res, jobs
 
 
+def cpu_numpy_port_sample(n_blocks, threads):
+    """the reference-STRUCTURED NumPy port (oracle/ref_numpy.py: materialised [S,B,D] candidates, two log_prob passes, full
+    argsort -- the op structure of rec/coding/beam_search_coder.py:53-122), block-parallel on `threads` host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ref_numpy as R
+    jobs = cpu_sample_jobs(n_blocks)
+    R.encode_block(*jobs[0], OMEGA, S, NBEAMS, SEED, n_aux=2)          # warm the tables
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(lambda j: R.encode_block(*j, OMEGA, S, NBEAMS, SEED), jobs))
+    dt = time.perf_counter() - t0
+    cand, cd, parts, _ = work_model([len(r[0]) for r in res], [BLOCK] * n_blocks)
+    return cand / dt, cd / dt, dt
+
+
 def cpu_sample_blocks(cores):
     """bounded CPU sample: ~0.4 s of single-core work per coder-block -> 10-20 s per step on all cores"""
     return int(min(1024, max(32 * cores, 64)))
+
+
+def workload_name():
+    return (f"BASELINE configs[3]: batch of {IMAGES_TOTAL} ImageNet32-shaped synthetic images x {LEVELS} resnet_vae latents "
+            f"[16,16,32], block_size {BLOCK}, beam_search n_beams={NBEAMS} extra_samples={EXTRA} (S={S}) kl_per_partition={OMEGA}")
+
+
+def config_dict(world):
+    """identical for the b200 arm and the reference arm of the same N"""
+    return {"workload": workload_name(), "images_total": IMAGES_TOTAL,
+            "parallelism": f"dp{world} (images sharded over the ranks, no collective in the loop)",
+            "l2": "inputs of one step (3.2 GB / N per GPU) exceed the 126 MB L2"}
 
 
 def run_reference(args):
@@ -136,7 +192,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_blocks = cpu_sample_blocks(cores)
     vals = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    for _ in range(1 if args.warmup > 0 else 0):
         cpu_port_sample(n_blocks, cores)
     t_all = 0.0
     for _ in range(args.steps):
@@ -147,33 +203,228 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "candidates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "sample": f"{n_blocks} coder-blocks of D=1000 per step"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(int(os.environ.get("WORLD_SIZE", "1"))),
         "candidate_dims_per_sec": float(np.mean([x[1] for x in vals])),
         "partitions_per_sec": float(np.mean([x[2] for x in vals])),
         "cpu_baseline": {"value": v, "unit": "candidates/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_blocks} coder-blocks (D=1000, S=36, B=20) per step, C oracle, {cores} threads"},
+                         "sample": f"{n_blocks} coder-blocks (D=1000, S=36, B=20) of the workload per step, C oracle "
+                                   f"(oracle/irec_oracle.c), {cores} threads"},
         "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
         "note": "TensorFlow 2.1/TFP 0.9 are not installable here; this is the C port of the reference algorithm "
-                "(oracle/irec_oracle.c) run block-parallel on all host threads",
+                "(oracle/irec_oracle.c) run block-parallel on all host threads -- a stronger CPU baseline than the "
+                "reference-structured NumPy port (bench.py's cpu_baselines[1])",
     }
     print(json.dumps(line))
 
 
-def workload_name():
-    return (f"C4-shaped: {IMAGES_PER_GPU} images/GPU x {LEVELS} resnet_vae latents [16,16,32], block_size {BLOCK}, "
-            f"beam_search n_beams={NBEAMS} extra_samples={EXTRA} (S={S}) kl_per_partition={OMEGA}")
+# ------------------------------------------------------------------------------------------------ C5: candidate-range sharding
+def c5_posterior(bits):
+    """SURVEY.md 8(d) C5 recipe: D=64 posterior vs N(0,I), mean scaled so that the block needs >= C5_MIN_AUX variables"""
+    import synth
+    omega = np.float32(bits * np.log(2.0))
+    mu, sig, pl, ps = synth.c1(C5_DIMS, data_seed=0)
+    mu64, sig64 = mu.astype(np.float64), sig.astype(np.float64)
+    kl0 = float(np.sum(0.5 * (mu64 ** 2 + sig64 ** 2 - 1) - np.log(sig64)))
+    need = C5_MIN_AUX * float(omega)
+    if kl0 < need:
+        base = float(np.sum(0.5 * (sig64 ** 2 - 1) - np.log(sig64)))
+        scale = np.sqrt(max(need - base, 0.0) / max(float(np.sum(0.5 * mu64 ** 2)), 1e-12)) * 1.02
+        mu = (mu * scale).astype(np.float32)
+    return omega, mu, sig, pl, ps
 
 
+def bench_c5(ctx, args):
+    """configs[4] under the driver's clock: per Omega one coder-block, every rank scores a contiguous candidate range, the
+    per-rank top-B records are exchanged (peer-memory stores, else NCCL all-gather) and merged identically on every rank;
+    the per-variable loop is replayed from a CUDA graph.  Times: CUDA events, mean over reps, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from irec_b200 import engine
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    out = []
+    for bits in C5_BITS:
+        omega, mu, sig, pl, ps = c5_posterior(bits)
+        S5 = int(np.exp(float(omega) * EXTRA))
+        d = [torch.as_tensor(a, device=dev).contiguous() for a in (mu, sig, pl, ps)]
+        blk = engine.ShardedBeamBlock(C5_DIMS, S5, NBEAMS, omega, max_aux=256, device=dev)
+        idx, sample = blk.encode(*d, seed=SEED)                   # eager: warm-up + result
+        idx_g, sample_g = blk.encode_graphed(*d, seed=SEED)       # captures the loop; must reproduce the eager result
+        graph_ok = bool(idx_g == idx and torch.equal(sample_g, sample))
+        times = []
+        for _ in range(args.c5_reps):
+            ctx["barrier"]()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n_aux = blk.init(*d, seed=SEED)
+            blk._graphs[n_aux].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms)
+        n_aux = len(idx)
+        cand = S5 + (n_aux - 1) * S5 * min(NBEAMS, S5)
+        rec = {"omega_bits": bits, "S": S5, "D": C5_DIMS, "n_beams": NBEAMS, "n_aux": n_aux, "ms": ms,
+               "candidates_per_sec": cand / (ms * 1e-3), "candidate_dims_per_sec": cand * C5_DIMS / (ms * 1e-3),
+               "exchange": ("peer-memory stores (irec_p2p_exchange)" if blk.p2p is not None else
+                            ("nccl all_gather" if world > 1 else "none")),
+               "cuda_graph": True, "graph_equals_eager": graph_ok}
+        if rank == 0:
+            if S5 <= 1.2e5:
+                from oracle import oracle as O
+                ref = O.beam_encode_block(mu, sig, pl, ps, omega, S5, NBEAMS, SEED, max_aux=256)
+                rec["matches_oracle"] = bool(idx == ref["indices"].tolist() and
+                                             np.array_equal(sample.cpu().numpy().view(np.uint32), ref["sample"].view(np.uint32)))
+            if world > 1 and bits == C5_BITS[-1]:
+                one = engine.ShardedBeamBlock(C5_DIMS, S5, NBEAMS, omega, max_aux=256, device=dev, single=True)
+                idx1, sample1 = one.encode(*d, seed=SEED)
+                rec["equals_1gpu_result"] = bool(idx1 == idx and torch.equal(sample1, sample))
+                del one
+        torch.cuda.synchronize()
+        blk._graphs.clear()
+        del blk
+        ctx["barrier"]()
+        out.append(rec)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak = world * sm_count * 128 * ctx["sm_max_mhz"] * 1e6
+    top = out[-1]
+    w = 10 + 24 / NBEAMS
+    return {"workload": "BASELINE configs[4]: one coder-block (D=64 posterior vs N(0,I)), candidate index range split over the "
+                        "ranks, top-B records exchanged and merged per auxiliary variable",
+            "n_gpus": world, "sweep": out,
+            "roofline": {"bound": "issue", "kernel": "k_gp_score_topb2<20>", "at_omega_bits": top["omega_bits"],
+                         "achieved": top["candidate_dims_per_sec"] * w / 1e9, "peak": peak / 1e9, "unit": "G lane-instr/s",
+                         "frac": top["candidate_dims_per_sec"] * w / peak,
+                         "work_model": "W = 10 + 24/B' lane-instr per candidate-dim, peak = N x SMs x 128 lanes x sm_max_mhz"}}
+
+
+# ------------------------------------------------------------------------------------------------ importance sampler
+def bench_is(ctx, args):
+    """GaussianCoder + ImportanceSampler (rec/coding/coder.py:493-584, importance_sampling.py:9-103): IS_IMAGES latents
+    [16,16,32] in total (sharded by images), block_size 1000, S = ceil(2^coding_bits) = 37; encode (plan + candidate table +
+    k_is_block, one packed D2H) and decode (k_is_decode), CUDA events, max over ranks"""
+    import torch
+    import torch.distributed as dist
+    import synth
+    from irec_b200 import engine as E, native as N
+    from irec_b200.sharding import unit_range
+    from rec.coding import GaussianCoder
+    from rec.coding.samplers import ImportanceSampler
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    lo, hi = unit_range(IS_IMAGES, rank, world)
+    n_img = hi - lo
+    coder = GaussianCoder(kl_per_partition=OMEGA, sampler=ImportanceSampler(coding_bits=OMEGA * EXTRA / np.log(2.0)), block_size=BLOCK)
+    S_is = coder.sampler.n_samples
+    arrs = [synth.c2(LATENT, data_seed=7000 + i) for i in range(lo, hi)]
+    tl, ts, pl, ps = (torch.from_numpy(np.stack([a[k] for a in arrs])).to(dev).reshape(-1) for k in range(4))
+    perm = coder._permutation(LATENT, SEED, dev)
+    gather = (perm[None, :] + torch.arange(n_img, device=dev)[:, None] * LATENT).reshape(-1).contiguous()
+    offsets, nb, max_dim = E.make_block_offsets(LATENT, BLOCK, dev, n_items=n_img)
+    dims = (offsets[1:] - offsets[:-1]).cpu().numpy()
+
+    def encode():
+        return E.is_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, coder.kl_per_partition, S_is, SEED)
+
+    indices, sample = encode()                      # warm-up + results (also settles the row-capacity hint)
+    n_aux = np.array([len(i) for i in indices])
+    cand, cd = int((n_aux * S_is).sum()), int((n_aux * S_is * dims).sum())
+    ctx["barrier"]()
+    l0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.is_reps):
+        encode()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = (N.launch_count() - l0) // args.is_reps
+    enc_ms = e0.elapsed_time(e1) / args.is_reps
+    dec = E.is_decode_blocks(pl, ps, gather, offsets, nb, max_dim, SEED, indices)
+    decode_ok = bool(torch.equal(dec, sample))
+    packed = E.pack_indices(indices, torch.int64, dev)
+    ws = torch.empty(int(N.lib().irec_is_block_workspace_bytes(packed[2])), dtype=torch.uint8, device=dev)
+    out = torch.empty_like(pl)
+    ctx["barrier"]()
+    t0 = time.perf_counter()
+    for _ in range(args.is_reps):
+        E.is_decode_blocks(pl, ps, gather, offsets, nb, max_dim, SEED, indices)
+    torch.cuda.synchronize()
+    dec_wall_ms = 1e3 * (time.perf_counter() - t0) / args.is_reps
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.is_reps):            # the launch alone, index rows already on the device
+        N.check(N.lib().irec_is_decode(N.ptr(pl), N.ptr(ps), N.ptr(gather), N.ptr(offsets), nb, int(max_dim), SEED, N.ptr(packed[0]),
+                                       packed[2], N.ptr(packed[1]), N.ptr(out), None, N.ptr(ws), ws.numel(), N.stream_ptr()), "irec_is_decode")
+    d1.record()
+    torch.cuda.synchronize()
+    dec_kernel_ms = d0.elapsed_time(d1) / args.is_reps
+    decode_ok = decode_ok and bool(torch.equal(out, sample))
+    t = torch.tensor([enc_ms, dec_wall_ms, dec_kernel_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([cand, cd, float(n_aux.sum()), nb], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    enc_ms, dec_wall_ms, dec_kernel_ms = (float(x) for x in t)
+    cand_all, cd_all, parts_all, nb_all = (float(x) for x in tot)
+    sec = enc_ms * 1e-3
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak = world * sm_count * 128 * ctx["sm_max_mhz"] * 1e6
+    res = {"workload": f"importance sampler: {IS_IMAGES} x [16,16,32] latents in total, block_size {BLOCK}, kl_per_partition {OMEGA}, "
+                       f"coding_bits {OMEGA * EXTRA / np.log(2.0):.3f} (S={S_is})",
+           "n_gpus": world, "coder_blocks": int(nb_all), "partitions": int(parts_all), "candidates": int(cand_all),
+           "encode_ms_per_call": enc_ms, "gpu_launches_per_call": int(launches),
+           "candidates_per_sec": cand_all / sec, "candidate_dims_per_sec": cd_all / sec, "partitions_per_sec": parts_all / sec,
+           "roofline": {"bound": "issue", "kernel": "k_is_block", "work_model": "W_IS = 34 lane-instr per candidate-dim (SURVEY.md 8d): "
+                        "Philox + Box-Muller + score per candidate-dim as the reference evaluates them; the kernel reads the launch-wide "
+                        "candidate table instead (4 B per candidate-dim from L2)",
+                        "achieved": cd_all * W_IS / sec / 1e9, "peak": peak / 1e9, "unit": "G lane-instr/s", "frac": cd_all * W_IS / sec / peak,
+                        "l2_read_gbs": cd_all * 4 / sec / 1e9 / world},
+           "decode_ms_per_call": dec_wall_ms, "decode_kernel_ms": dec_kernel_ms, "decode_bit_exact": decode_ok}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        n_cpu = min(nb, max(64, 4 * cores))
+        hp = perm.cpu().numpy()
+        tlh, tsh, plh, psh = (x.cpu().numpy() for x in (tl, ts, pl, ps))
+        smp = sample.cpu().numpy()
+        nblk_img = nb // n_img
+
+        def one(b):
+            img, k = divmod(b, nblk_img)
+            sel = img * LATENT + hp[k * BLOCK:min(LATENT, (k + 1) * BLOCK)]
+            ref = O.is_encode_block(tlh[sel], tsh[sel], plh[sel], psh[sel], OMEGA, S_is, SEED)
+            ok = [int(i) for i in ref["indices"]] == [int(i) for i in indices[b]] and \
+                np.array_equal(np.asarray(ref["sample"], np.float32).view(np.uint32), smp[sel].view(np.uint32))
+            return len(ref["indices"]) * S_is, int(ok)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            rr = list(ex.map(one, range(n_cpu)))
+        dt = time.perf_counter() - t0
+        res["blocks_identical_to_oracle"] = f"{sum(r[1] for r in rr)}/{n_cpu}"
+        res["index_match_pct"] = 100.0 * sum(r[1] for r in rr) / n_cpu
+        res["cpu_baseline"] = {"value": sum(r[0] for r in rr) / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
+                               "sample": f"{n_cpu} coder-blocks of the same workload, C oracle, {cores} threads, {dt:.1f} s"}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--images-per-gpu", type=int, default=IMAGES_PER_GPU)
+    ap.add_argument("--images-total", type=int, default=IMAGES_TOTAL, help="configs[3] is 1024; smaller values are for kernel-tuning runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel-tuning runs: skip the end-to-end leg")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-is", action="store_true")
+    ap.add_argument("--c5-reps", type=int, default=3)
+    ap.add_argument("--is-reps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,6 +434,7 @@ def main():
     import __graft_entry__ as g
     g.build()
     from irec_b200 import engine as E, native as N, Normal
+    from irec_b200.sharding import unit_range
     from rec.coding import BeamSearchCoder
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,13 +444,32 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_img = args.images_per_gpu
+    images_total = args.images_total
+    img_lo, img_hi = unit_range(images_total, rank, world)
+    n_img = img_hi - img_lo
+    assert n_img > 0, "more ranks than images"
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ctx = {"dev": dev, "rank": rank, "world": world, "barrier": barrier, "sm_max_mhz": sm_max_mhz}
 
     # ---------------- synthetic inputs (pinned host + device copies) ----------------
+    cores = os.cpu_count() or 1
+    levels = synth_levels(list(range(img_lo, img_hi)), max(1, cores // max(1, min(world, 8))))
     host = []      # per level: 4 pinned tensors [n_img, LATENT]
     for lvl in range(LEVELS):
-        arrs = [synth_level(rank * n_img + i, lvl) for i in range(n_img)]
+        arrs = levels[lvl]
         host.append([torch.from_numpy(np.stack([a[k] for a in arrs])).pin_memory() for k in range(4)])
+    del levels
     devt = [[t.to(dev, non_blocking=True) for t in lv] for lv in host]
     coder = BeamSearchCoder(kl_per_partition=OMEGA, n_beams=NBEAMS, extra_samples=EXTRA, block_size=BLOCK)
     perm = coder._permutation(LATENT, SEED, dev)
@@ -213,6 +484,8 @@ def main():
     out_st = [torch.empty(nb, dtype=torch.int32, device=dev) for _ in range(LEVELS)]
     out_sample = [torch.empty(n_img * LATENT, dtype=torch.float32, device=dev) for _ in range(LEVELS)]
     stream = N.stream_ptr()
+    path = int(lib.irec_beam_encode_path(nb, max_dim, S, NBEAMS))
+    kernel_name = {2: "k_beam_encode_resident2<20>", 3: "k_beam_encode_tmem<20>", 1: "k_beam_encode_resident<20>"}.get(path, f"path {path}")
 
     def launch_level(lvl):
         tl, ts, pl, ps = (t.reshape(-1) for t in devt[lvl])
@@ -230,12 +503,6 @@ def main():
             if events is not None:
                 e1.record()
                 events.append((e0, e1))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
     for _ in range(args.warmup):
@@ -295,65 +562,72 @@ def main():
         step_e2e()
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 2))
-        for _ in range(e2e_steps):
+        for _ in range(args.steps):
             parts_e2e, _ = step_e2e()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_s = (time.perf_counter() - t0) / args.steps
         assert parts_e2e == parts, (parts_e2e, parts)
+        for lvl in (0, LEVELS - 1):
+            assert torch.equal(sample_host[lvl].reshape(-1), out_sample[lvl].cpu()), "e2e sample differs from the resident run"
     h2d = LEVELS * 4 * n_img * LATENT * 4
-    d2h = LEVELS * (n_img * LATENT * 4 + nb * (2 + int(na_all.max())) * 4)
+    d2h = LEVELS * (n_img * LATENT * 4 + nb * (2 + int(E._hint_get((str(dev), float(OMEGA))))) * 4)
 
     # ---------------- max over ranks, sums over ranks ----------------
     t_res = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    tot = torch.tensor([cand, cd, parts], dtype=torch.float64, device=dev)
+    tot = torch.tensor([cand, cd, parts, h2d, d2h, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_total, e2e_ms = float(t_res[0]), float(t_res[1])
-    cand_all, cd_all, parts_all = (float(x) for x in tot)
+    cand_all, cd_all, parts_all, h2d_all, d2h_all, launches_all = (float(x) for x in tot)
     sec = ms_total * 1e-3 / args.steps
 
+    # free the headline workload before the sub-benches
+    del devt, out_idx, out_sample, host, sample_host
+    torch.cuda.empty_cache()
+    c5 = None if args.no_c5 else bench_c5(ctx, args)
+    isb = None if args.no_is else bench_is(ctx, args)
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         peak_instr = sm_count * 128 * sm_max_mhz * 1e6
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes_level = float(16 * dims.sum() + 4 * dims.sum() + 4 * na_all.mean(axis=0).sum())
-        # measured per-launch DRAM traffic and shared-memory wavefronts per candidate-dim of the same launch shape,
-        # from the committed `ncu --set full` capture (profiles/r1_bench_launch_ncu.json)
+        # measured per-launch DRAM traffic and shared-memory wavefronts per candidate-dim of the same kernel, from the
+        # committed `ncu --set full` capture (profiles/<round>_bench_launch_ncu.json)
         traffic, traffic_src, wf_per_cd = None, None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_launch_ncu.json")))
-            if prof.get("images_per_gpu") == n_img:
-                traffic = float(prof["dram_bytes_read"] + prof["dram_bytes_write"])
-            wf_per_cd = float(prof["shared_wavefronts"]) / float(prof["candidate_dims"])
-            traffic_src = prof.get("source")
-        except Exception:
-            pass
+        for name in ("r2_bench_launch_ncu.json", "r1_bench_launch_ncu.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if prof.get("kernel", "k_beam_encode_resident2<20>") != kernel_name:
+                    continue
+                if prof.get("images_per_gpu") == n_img:
+                    traffic = float(prof["dram_bytes_read"] + prof["dram_bytes_write"])
+                else:       # other launch size: scale the measured bytes per candidate-dim
+                    traffic = float(prof["dram_bytes_read"] + prof["dram_bytes_write"]) / float(prof["candidate_dims"]) * (cd / LEVELS)
+                wf_per_cd = float(prof["shared_wavefronts"]) / float(prof["candidate_dims"])
+                traffic_src = prof.get("source")
+                break
+            except Exception:
+                continue
         smem_rate = (cd_all / world / sec) * wf_per_cd if wf_per_cd else float("nan")
         line = {
             "metric": METRIC, "value": cand_all / sec, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "images_total": n_img * world, "parallelism": f"dp{world} (images sharded, no collective in the loop)",
-                       "l2": "inputs of one step (403 MB/GPU) exceed the 126 MB L2"},
+            "config": dict(config_dict(world), images_total=images_total),
             "candidate_dims_per_sec": cd_all / sec, "partitions_per_sec": parts_all / sec,
             "index_match_pct": None,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches_all),
+            "build_mode": g.BUILD_MODE,
             "clocks": clock_info,
-            "e2e": {"value": cand_all / (e2e_ms * 1e-3), "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "roofline": {"bound": "issue", "kernel": "k_beam_encode_resident2<20>", "achieved": achieved_instr / 1e9,
+            "e2e": {"value": cand_all / (e2e_ms * 1e-3), "unit": "candidates/s", "h2d_bytes_per_step": int(h2d_all),
+                    "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms, "steps": args.steps},
+            "roofline": {"bound": "issue", "kernel": kernel_name, "achieved": achieved_instr / 1e9,
                          "peak": peak_instr / 1e9, "unit": "G lane-instr/s", "frac": achieved_instr / peak_instr,
                          "peak_source": f"{sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
                          "work_model": "W = 10 + 24/B' lane-instr per candidate-dim (SURVEY.md 8d)",
-                         "avg_launch_ms": kernel_ms_avg, "traffic": traffic, "traffic_source": traffic_src,
+                         "avg_launch_ms": kernel_ms_avg, "blocks_per_launch": int(nb), "traffic": traffic, "traffic_source": traffic_src,
                          "smem": {"wavefronts_per_candidate_dim": wf_per_cd, "achieved_gwf_s": smem_rate / 1e9,
                                   "peak_gwf_s": sm_count * sm_max_mhz * 1e6 / 1e9,
                                   "frac": smem_rate / (sm_count * sm_max_mhz * 1e6), "source": traffic_src},
@@ -361,30 +635,62 @@ def main():
                                  "frac": alg_bytes_level / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_launch": alg_bytes_level}},
         }
+        if c5 is not None:
+            line["c5"] = c5
+        if isb is not None:
+            line["is"] = isb
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
             n_blocks = cpu_sample_blocks(cores)
             v, cdv, pv, dt, res, jobs = cpu_port_sample(n_blocks, cores)
             line["cpu_baseline"] = {"value": v, "unit": "candidates/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_blocks} coder-blocks (D=1000, S=36, B=20) of the same workload, C oracle "
                                               f"(oracle/irec_oracle.c), {cores} threads, {dt:.1f} s",
                                     "candidate_dims_per_sec": cdv}
-            # index match against the oracle on the same sample blocks (free-running)
-            match, total = 0, 0
-            idx0 = [o.cpu().numpy() for o in out_idx]
-            na0 = [o.cpu().numpy() for o in out_na]
-            for i, r in enumerate(res):
-                img, lvl, b = i // 8, i % LEVELS, i % 8
-                if img >= n_img:
-                    continue
-                blk = img * 9 + b
-                got = idx0[lvl][blk, :na0[lvl][blk]]
-                total += len(r["indices"])
-                match += int((got == r["indices"]).sum()) if len(got) == len(r["indices"]) else 0
-            line["index_match_pct"] = 100.0 * match / max(total, 1)
+            n_np = max(cores, 16)
+            v2, cd2, dt2 = cpu_numpy_port_sample(n_np, cores)
+            line["cpu_baselines"] = [line["cpu_baseline"],
+                                     {"value": v2, "unit": "candidates/s", "cores": cores, "kind": "port",
+                                      "sample": f"{n_np} coder-blocks of the same workload, reference-structured NumPy port "
+                                                f"(oracle/ref_numpy.py: [S,B,D] candidate tensor, two log_prob passes, argsort), "
+                                                f"{cores} threads, {dt2:.1f} s", "candidate_dims_per_sec": cd2}]
+            # index match against the oracle on the same sample blocks (free-running): the sampled blocks are coded again
+            line.update(index_match(res, jobs, coder))
+            # canonical score vs the reference's own float32 form (oracle/refform_study.py), bounded live sample
+            from oracle import refform_study as RS
+            rep = RS.run(max(2 * cores, 32), threads=cores)
+            line["refform"] = {"blocks": rep["blocks"], "index_match_pct_refform": rep["free_running"]["index_match_pct_refform"],
+                               "blocks_identical_pct": rep["free_running"]["blocks_identical_pct"],
+                               "teacher_forced_match_pct": rep["teacher_forced"]["teacher_forced_match_pct"],
+                               "teacher_forced_partitions": rep["teacher_forced"]["partitions"],
+                               "worst_relative_gap_of_a_mismatch": rep["teacher_forced"]["worst_relative_gap_of_a_mismatch"],
+                               "n_aux_differs_float32_kl": rep["kl_float32_vs_float64"]["blocks_n_aux_differs_pairwise"],
+                               "population": "profiles/r2_refform_study.json (2048 coder-blocks)", "seconds": rep["seconds"]}
+            line["index_match_pct_refform"] = rep["free_running"]["index_match_pct_refform"]
+            line["teacher_forced_match_pct"] = rep["teacher_forced"]["teacher_forced_match_pct"]
         print(json.dumps(line))
     if world > 1:
+        barrier()
         dist.destroy_process_group()
+
+
+def index_match(res, jobs, coder):
+    """GPU == oracle on the CPU sample's coder-blocks: the blocks are coded again in one launch (one block per row)"""
+    import torch
+    from irec_b200 import engine as E
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nbk = len(jobs)
+    flat = [torch.from_numpy(np.concatenate([j[k] for j in jobs])).to(dev) for k in range(4)]
+    offsets, nb, max_dim = E.make_block_offsets(nbk * BLOCK, BLOCK, dev)
+    out = E.beam_encode_blocks(*flat, None, offsets, nb, max_dim, OMEGA, S, NBEAMS, SEED)
+    smp = out.sample.cpu().numpy()
+    match = total = blocks = 0
+    for b, r in enumerate(res):
+        ref_idx = r["indices"].tolist()
+        total += len(ref_idx)
+        same = out.indices[b] == ref_idx
+        match += len(ref_idx) if same else sum(int(x == y) for x, y in zip(out.indices[b], ref_idx))
+        blocks += int(same and np.array_equal(smp[b * BLOCK:(b + 1) * BLOCK].view(np.uint32), r["sample"].view(np.uint32)))
+    return {"index_match_pct": 100.0 * match / max(total, 1), "blocks_bit_identical_to_oracle": f"{blocks}/{nbk}"}
 
 
 if __name__ == "__main__":

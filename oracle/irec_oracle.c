@@ -678,6 +678,270 @@ double orc_beam_score_constant(const float* t_loc, const float* t_scale, const f
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Population study: the canonical log-weight (centred quadratic, fixed reduction tree) against the reference's OWN
+ * form (beam_search_coder.py:79-106): per candidate  reduce_sum_d( lp(x; m, sqrt(s2)) - lp(x; 0, sqrt(tot)) )  in
+ * float32 with TFP's Normal._log_prob, then argsort DESCENDING.  TensorFlow's reduce_sum order over the last axis is
+ * an Eigen implementation detail, so the sum is evaluated in three ways (sum_mode):
+ *   0 = sequential float32,  1 = pairwise float32 (8 lanes, blocks of 128: NumPy's scheme),  2 = float64 accumulator.
+ * Two comparisons per coder-block:
+ *   free-running   : the reference-form coder runs on its own beam state; its indices vs the canonical indices;
+ *   teacher-forced : at every partition of the CANONICAL run, reference-form scores of the same state; the kept set
+ *                    (top-B) vs the canonical kept set.  When they differ, gap = the largest |w_in - w_out| over the
+ *                    swapped candidates, relative to max |w| of the kept set, measured in the reference form (float64
+ *                    accumulation): north_star's 1e-5 tolerance applies to it.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_aux;
+    int32_t free_identical;          /* reference-form indices == canonical indices */
+    int32_t free_first_diff;         /* first differing partition (or -1) */
+    int32_t tf_partitions;           /* partitions compared teacher-forced */
+    int32_t tf_set_mismatch;         /* partitions whose kept SET differs */
+    int32_t tf_order_mismatch;       /* partitions whose kept set is equal but ordered differently */
+    int32_t tf_best_mismatch;        /* partitions whose FIRST (best) candidate differs */
+    int32_t pad;
+    double tf_max_rel_gap;           /* worst relative gap over the set mismatches (0 when none) */
+    double max_rel_score_dev;        /* max |canonical + const - refform64| / max(1, |refform64|) over all candidates */
+    double max_dev_canon_exact;      /* max |canonical + const - exact| / max(1, |exact|): exact = the log-ratio in float64 throughout */
+    double max_dev_ref32_exact;      /* max |reference float32 form (sum_mode) + const' - exact| / max(1, |exact|) */
+} orc_refform_stats_t;
+
+static float refform_sum(const float* term, int D, int sum_mode)
+{
+    if (sum_mode == 0) {
+        float a = 0.0f;
+        for (int d = 0; d < D; ++d) a = a + term[d];
+        return a;
+    }
+    if (sum_mode == 2) {
+        double a = 0.0;
+        for (int d = 0; d < D; ++d) a += (double)term[d];
+        return (float)a;
+    }
+    /* NumPy pairwise_sum for float32 (npy PW_BLOCKSIZE 128, 8 accumulators) */
+    float stack[64];
+    int sp = 0, cnt = 0;
+    for (int base = 0; base < D; base += 128) {
+        int n = D - base < 128 ? D - base : 128;
+        float blk;
+        if (n < 8) {
+            blk = 0.0f;
+            for (int i = 0; i < n; ++i) blk = blk + term[base + i];
+        } else {
+            float r[8];
+            for (int j = 0; j < 8; ++j) r[j] = term[base + j];
+            int i;
+            for (i = 8; i + 8 <= n; i += 8)
+                for (int j = 0; j < 8; ++j) r[j] = r[j] + term[base + i + j];
+            blk = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            for (; i < n; ++i) blk = blk + term[base + i];
+        }
+        stack[sp++] = blk;
+        ++cnt;
+        for (int c = cnt; (c & 1) == 0; c >>= 1) { stack[sp - 2] = stack[sp - 2] + stack[sp - 1]; --sp; }
+    }
+    while (sp > 1) { stack[sp - 2] = stack[sp - 2] + stack[sp - 1]; --sp; }
+    return sp ? stack[0] : 0.0f;
+}
+
+/* reference-form scores of one partition for an explicit state; ref64 (may be NULL): the same sums accumulated in double */
+static void refform_scores(const float* T, const float* sa, const float* m, const float* s2, const float* tot,
+                           const float* beams, const int32_t* hsum, int D, int S, int Bcur, int64_t q, int sum_mode,
+                           float* scores, double* ref64, double* exact64)
+{
+    int32_t* r = (int32_t*)malloc(sizeof(int32_t) * (size_t)D);
+    float* term = (float*)malloc(sizeof(float) * (size_t)D);
+    float* qs = (float*)malloc(sizeof(float) * (size_t)D);
+    float* cs = (float*)malloc(sizeof(float) * (size_t)D);
+    float* qb = (float*)malloc(sizeof(float) * (size_t)D);
+    float* qn = (float*)malloc(sizeof(float) * (size_t)D);
+    float* cn = (float*)malloc(sizeof(float) * (size_t)D);
+    const float half_log_2pi = (float)(0.5 * log(2.0 * 3.14159265358979323846));
+    for (int d = 0; d < D; ++d) {
+        qs[d] = sqrtf(s2[d]); cs[d] = sqrtf(tot[d]);
+        qb[d] = m[d] / qs[d];
+        qn[d] = half_log_2pi + c_logf(qs[d]);
+        cn[d] = half_log_2pi + c_logf(cs[d]);
+    }
+    for (int s = 0; s < S; ++s) {
+        orc_beam_uniform_int(q, (int64_t)s * D, D, r);
+        for (int b = 0; b < Bcur; ++b) {
+            const int32_t h = hash_from_sum(hsum[b]);
+            const float* beam = beams ? beams + (size_t)b * D : NULL;
+            double a64 = 0.0, e64 = 0.0;
+            for (int d = 0; d < D; ++d) {
+                float x = (beam ? beam[d] : 0.0f) + beam_candidate(T, r[d], h, sa[d]);
+                if (exact64) {       /* log N(x; m, s2) - log N(x; 0, tot), float64 throughout from the float32 schedule values */
+                    double dx = (double)x - (double)m[d];
+                    e64 += -0.5 * dx * dx / (double)s2[d] + 0.5 * (double)x * (double)x / (double)tot[d]
+                           - 0.5 * log((double)s2[d]) + 0.5 * log((double)tot[d]);
+                }
+                float dq = x / qs[d] - qb[d];
+                float dc = x / cs[d] - 0.0f / cs[d];
+                float lq = -0.5f * (dq * dq) - qn[d];
+                float lc = -0.5f * (dc * dc) - cn[d];
+                term[d] = lq - lc;
+                a64 += (double)term[d];
+            }
+            scores[(size_t)s * Bcur + b] = refform_sum(term, D, sum_mode);
+            if (ref64) ref64[(size_t)s * Bcur + b] = a64;
+            if (exact64) exact64[(size_t)s * Bcur + b] = e64;
+        }
+    }
+    free(r); free(term); free(qs); free(cs); free(qb); free(qn); free(cn);
+}
+
+static void commit_winners(const float* T, const float* sa, const int64_t* top, int keep, int Bcur, int D, int n_aux, int t,
+                           int64_t q, float** beams, float** nbeams, int32_t** hsum, int32_t** nhsum, int32_t** hist,
+                           int32_t** nhist, int32_t* r)
+{
+    for (int j = 0; j < keep; ++j) {
+        int s = (int)(top[j] / Bcur), b = (int)(top[j] % Bcur);
+        orc_beam_uniform_int(q, (int64_t)s * D, D, r);
+        int32_t h = hash_from_sum((*hsum)[b]);
+        for (int d = 0; d < D; ++d)
+            (*nbeams)[(size_t)j * D + d] = (t == 0 ? 0.0f : (*beams)[(size_t)b * D + d]) + beam_candidate(T, r[d], h, sa[d]);
+        memcpy(*nhist + (size_t)j * n_aux, *hist + (size_t)b * n_aux, sizeof(int32_t) * (size_t)t);
+        (*nhist)[(size_t)j * n_aux + t] = s;
+        (*nhsum)[j] = hsum_extend((*hsum)[b], s, t);
+    }
+    float* tf_ = *beams; *beams = *nbeams; *nbeams = tf_;
+    int32_t* ti = *hist; *hist = *nhist; *nhist = ti;
+    ti = *hsum; *hsum = *nhsum; *nhsum = ti;
+}
+
+int orc_beam_refform_study(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale, int D,
+                           float omega, int S, int B, int64_t seed, int sum_mode, int32_t* idx_canon, int32_t* idx_ref,
+                           int max_aux, orc_refform_stats_t* st)
+{
+    static float T[IREC_PRIME];
+    static int T_ready = 0;
+    if (!T_ready) { orc_ndtri_table(T); T_ready = 1; }
+    memset(st, 0, sizeof(*st));
+    st->free_first_diff = -1;
+    const float kl = orc_kl(t_loc, t_scale, p_loc, p_scale, D);
+    const int n_aux = orc_n_aux(kl, omega);
+    st->n_aux = n_aux;
+    if (n_aux <= 0) return 1;
+    if (n_aux > max_aux) return 2;
+
+    float* sa = (float*)malloc(sizeof(float) * D); float* A = (float*)malloc(sizeof(float) * D);
+    float* E = (float*)malloc(sizeof(float) * D); float* M = (float*)malloc(sizeof(float) * D);
+    float* s2 = (float*)malloc(sizeof(float) * D); float* tot = (float*)malloc(sizeof(float) * D);
+    float* scores = (float*)malloc(sizeof(float) * (size_t)S * B);
+    float* rscores = (float*)malloc(sizeof(float) * (size_t)S * B);
+    double* r64 = (double*)malloc(sizeof(double) * (size_t)S * B);
+    double* x64 = (double*)malloc(sizeof(double) * (size_t)S * B);
+    int64_t* top = (int64_t*)malloc(sizeof(int64_t) * B);
+    int64_t* rtop = (int64_t*)malloc(sizeof(int64_t) * B);
+    int32_t* r = (int32_t*)malloc(sizeof(int32_t) * D);
+
+    for (int pass = 0; pass < 2; ++pass) {          /* 0: canonical run + teacher-forced comparison, 1: free-running reference form */
+        float* cum = (float*)calloc((size_t)D, sizeof(float));
+        float* beams = (float*)calloc((size_t)B * D, sizeof(float));
+        float* nbeams = (float*)calloc((size_t)B * D, sizeof(float));
+        int32_t* hsum = (int32_t*)calloc((size_t)B, sizeof(int32_t));
+        int32_t* nhsum = (int32_t*)calloc((size_t)B, sizeof(int32_t));
+        int32_t* hist = (int32_t*)calloc((size_t)B * n_aux, sizeof(int32_t));
+        int32_t* nhist = (int32_t*)calloc((size_t)B * n_aux, sizeof(int32_t));
+        int Bcur = 1;
+        for (int t = 0; t < n_aux; ++t) {
+            beam_schedule_step(t_loc, t_scale, p_loc, p_scale, D, orc_aux_ratio(n_aux - 1 - t), cum, sa, A, E, M, s2, tot);
+            const int64_t q = seed + t;
+            const int64_t ncand = (int64_t)S * Bcur;
+            const int keep = (int)(ncand < B ? ncand : B);
+            if (pass == 0) {
+                orc_beam_scores(T, sa, A, E, M, t == 0 ? NULL : beams, hsum, D, S, Bcur, q, scores);
+                refform_scores(T, sa, M, s2, tot, t == 0 ? NULL : beams, hsum, D, S, Bcur, q, sum_mode, rscores, r64, x64);
+                top_k_desc(scores, ncand, keep, top);
+                top_k_desc(rscores, ncand, keep, rtop);
+                /* canonical = reference form - per-partition constant: compare through the differences to the best */
+                double wmax = 0.0;
+                for (int j = 0; j < keep; ++j) { double w = fabs(r64[top[j]]); if (w > wmax) wmax = w; }
+                if (wmax < 1.0) wmax = 1.0;
+                {
+                    const double c = r64[top[0]] - (double)scores[top[0]];
+                    for (int64_t i = 0; i < ncand; ++i) {
+                        if (!(scores[i] == scores[i]) || isinf(scores[i])) continue;
+                        double dev = fabs(((double)scores[i] + c) - r64[i]) / (fabs(r64[i]) > 1.0 ? fabs(r64[i]) : 1.0);
+                        if (dev > st->max_rel_score_dev) st->max_rel_score_dev = dev;
+                    }
+                    /* against the exact value: the canonical form drops a per-partition constant (fixed through the best
+                       candidate); the float32 reference form carries its own constant */
+                    const double ce = x64[top[0]] - (double)scores[top[0]];
+                    const double cr = x64[top[0]] - (double)rscores[top[0]];
+                    for (int64_t i = 0; i < ncand; ++i) {
+                        if (!(scores[i] == scores[i]) || isinf(scores[i])) continue;
+                        const double den = fabs(x64[i]) > 1.0 ? fabs(x64[i]) : 1.0;
+                        double d1 = fabs(((double)scores[i] + ce) - x64[i]) / den;
+                        double d2 = fabs(((double)rscores[i] + cr) - x64[i]) / den;
+                        if (d1 > st->max_dev_canon_exact) st->max_dev_canon_exact = d1;
+                        if (d2 > st->max_dev_ref32_exact) st->max_dev_ref32_exact = d2;
+                    }
+                }
+                st->tf_partitions++;
+                int same_order = 1, same_set = 1;
+                for (int j = 0; j < keep; ++j) if (top[j] != rtop[j]) same_order = 0;
+                if (!same_order) {
+                    double gap = 0.0;
+                    for (int j = 0; j < keep; ++j) {
+                        int in_r = 0, in_c = 0;
+                        for (int k = 0; k < keep; ++k) { if (rtop[k] == top[j]) in_r = 1; if (top[k] == rtop[j]) in_c = 1; }
+                        if (!in_r || !in_c) same_set = 0;
+                    }
+                    if (!same_set) {
+                        /* swapped candidates: those kept by exactly one side; the gap is the spread of their reference-form weights */
+                        double lo = 1e300, hi = -1e300;
+                        for (int j = 0; j < keep; ++j) {
+                            int in_r = 0, in_c = 0;
+                            for (int k = 0; k < keep; ++k) { if (rtop[k] == top[j]) in_r = 1; if (top[k] == rtop[j]) in_c = 1; }
+                            if (!in_r) { double w = r64[top[j]]; if (w < lo) lo = w; if (w > hi) hi = w; }
+                            if (!in_c) { double w = r64[rtop[j]]; if (w < lo) lo = w; if (w > hi) hi = w; }
+                        }
+                        gap = (hi - lo) / wmax;
+                        if (gap > st->tf_max_rel_gap) st->tf_max_rel_gap = gap;
+                        st->tf_set_mismatch++;
+                    } else {
+                        st->tf_order_mismatch++;
+                    }
+                    if (top[0] != rtop[0]) st->tf_best_mismatch++;
+                }
+                commit_winners(T, sa, top, keep, Bcur, D, n_aux, t, q, &beams, &nbeams, &hsum, &nhsum, &hist, &nhist, r);
+            } else {
+                refform_scores(T, sa, M, s2, tot, t == 0 ? NULL : beams, hsum, D, S, Bcur, q, sum_mode, rscores, NULL, NULL);
+                top_k_desc(rscores, ncand, keep, rtop);
+                commit_winners(T, sa, rtop, keep, Bcur, D, n_aux, t, q, &beams, &nbeams, &hsum, &nhsum, &hist, &nhist, r);
+            }
+            Bcur = keep;
+        }
+        int32_t* out = pass == 0 ? idx_canon : idx_ref;
+        for (int t = 0; t < n_aux; ++t) out[t] = hist[t];
+        free(cum); free(beams); free(nbeams); free(hsum); free(nhsum); free(hist); free(nhist);
+    }
+    st->free_identical = 1;
+    for (int t = 0; t < n_aux; ++t)
+        if (idx_canon[t] != idx_ref[t]) { st->free_identical = 0; st->free_first_diff = t; break; }
+    free(sa); free(A); free(E); free(M); free(s2); free(tot); free(scores); free(rscores); free(r64); free(x64); free(top); free(rtop); free(r);
+    return 0;
+}
+
+/* KL in float32 the way TFP 0.9 kl_normal_normal evaluates it (coder.py:499, beam_search_coder.py:57), summed in float32
+ * (sum_mode as above) -- to count the blocks whose n_aux differs from the canonical float64 KL */
+float orc_kl_f32(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale, int D, int sum_mode)
+{
+    float* term = (float*)malloc(sizeof(float) * (size_t)D);
+    for (int d = 0; d < D; ++d) {
+        float dl = c_logf(t_scale[d]) - c_logf(p_scale[d]);
+        float a = t_loc[d] / p_scale[d], b = p_loc[d] / p_scale[d];
+        float sq = (a - b) * (a - b);
+        float em = (float)expm1((double)(2.0f * dl));
+        term[d] = (0.5f * sq + 0.5f * em) - dl;
+    }
+    float r = refform_sum(term, D, sum_mode);
+    free(term);
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Importance sampler  (importance_sampling.py:9-103) and GaussianCoder blocks (coder.py:493-584)
  * ---------------------------------------------------------------------------------------- */
 /* importance_sampling.py:51  S = int32(ceil(exp(coding_bits * log(2.)))) -- canonical: float32 product,

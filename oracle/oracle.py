@@ -38,6 +38,7 @@ def lib():
         _lib.orc_is_coded_sample.restype = C.c_int64
         _lib.orc_beam_refform_logw.restype = C.c_double
         _lib.orc_beam_score_constant.restype = C.c_double
+        _lib.orc_kl_f32.restype = C.c_float
     return _lib
 
 
@@ -170,6 +171,41 @@ def top_k_desc(v, k):
 # ------------------------------------------------------------------------------------- beam coder
 class OracleError(Exception):
     pass
+
+
+class RefformStats(C.Structure):
+    """orc_refform_stats_t (irec_oracle.c)"""
+    _fields_ = [("n_aux", C.c_int32), ("free_identical", C.c_int32), ("free_first_diff", C.c_int32),
+                ("tf_partitions", C.c_int32), ("tf_set_mismatch", C.c_int32), ("tf_order_mismatch", C.c_int32),
+                ("tf_best_mismatch", C.c_int32), ("pad", C.c_int32), ("tf_max_rel_gap", C.c_double),
+                ("max_rel_score_dev", C.c_double), ("max_dev_canon_exact", C.c_double), ("max_dev_ref32_exact", C.c_double)]
+
+
+SUM_MODES = {"sequential": 0, "pairwise": 1, "float64": 2}
+
+
+def beam_refform_study(t_loc, t_scale, p_loc, p_scale, omega, S, B, seed, sum_mode="pairwise", max_aux=4096):
+    """canonical coder vs the reference's two-log_prob float32 form on one coder-block, free-running and teacher-forced
+    (orc_beam_refform_study).  Returns a dict of the statistics plus both index lists."""
+    tl, ts, pl, ps = map(_f32, (t_loc, t_scale, p_loc, p_scale))
+    ic = np.zeros(max_aux, np.int32)
+    ir = np.zeros(max_aux, np.int32)
+    st = RefformStats()
+    rc = lib().orc_beam_refform_study(_p(tl), _p(ts), _p(pl), _p(ps), C.c_int(tl.size), C.c_float(omega), C.c_int(S), C.c_int(B),
+                                      C.c_int64(seed), C.c_int(SUM_MODES[sum_mode]), _p(ic, C.c_int32), _p(ir, C.c_int32),
+                                      C.c_int(max_aux), C.byref(st))
+    if rc != 0:
+        raise OracleError(f"orc_beam_refform_study rc={rc} (n_aux={st.n_aux})")
+    out = {name: getattr(st, name) for name, _ in RefformStats._fields_ if name != "pad"}
+    out["indices_canonical"] = ic[:st.n_aux].copy()
+    out["indices_refform"] = ir[:st.n_aux].copy()
+    return out
+
+
+def kl_f32(t_loc, t_scale, p_loc, p_scale, sum_mode="pairwise"):
+    """KL(target || coder) the way TFP evaluates it in float32 (irec_oracle.c orc_kl_f32)"""
+    tl, ts, pl, ps = map(_f32, (t_loc, t_scale, p_loc, p_scale))
+    return float(lib().orc_kl_f32(_p(tl), _p(ts), _p(pl), _p(ps), C.c_int(tl.size), C.c_int(SUM_MODES[sum_mode])))
 
 
 def beam_num_samples(kl_per_partition, extra_samples):

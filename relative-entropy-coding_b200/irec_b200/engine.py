@@ -194,19 +194,22 @@ def beam_encode_blocks(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets
 
 
 def pack_indices(indices, dtype, device):
-    """per-block index lists -> ([nb, max_aux] tensor, [nb] counts, max_aux) with ONE host->device copy (counts in the
-    first column of the staging array)"""
+    """per-block index lists -> ([nb, max_aux] tensor, [nb] counts, max_aux): one flat conversion of the Python ints, one
+    vectorised scatter into the padded rows, ONE host->device copy (counts ride in the first column)"""
+    import itertools
     import numpy as np
     nb = len(indices)
-    lens = [len(i) for i in indices]
-    max_aux = max(1, max(lens) if lens else 1)
     np_dtype = np.int64 if dtype == torch.int64 else np.int32
+    lens = np.fromiter((len(i) for i in indices), np.int64, count=nb)
+    total = int(lens.sum())
+    max_aux = max(1, int(lens.max()) if nb else 1)
     host = np.zeros((nb, max_aux + 1), dtype=np_dtype)
-    for b, ind in enumerate(indices):
-        k = lens[b]
-        host[b, 0] = k
-        if k:
-            host[b, 1:k + 1] = np.asarray(ind, dtype=np_dtype) if not isinstance(ind, np.ndarray) else ind.astype(np_dtype, copy=False)
+    host[:, 0] = lens
+    if total:
+        flat = np.fromiter(itertools.chain.from_iterable(indices), np_dtype, count=total)
+        rows = np.repeat(np.arange(nb), lens)
+        cols = np.arange(total) - np.repeat(np.cumsum(lens) - lens, lens) + 1
+        host[rows, cols] = flat
     both = torch.from_numpy(host).to(device)
     idx = both[:, 1:].contiguous()
     n = both[:, 0].to(torch.int32).contiguous()
@@ -361,9 +364,11 @@ def uniform_int_stream(global_seed, op_seed, lo, hi, start, n, device="cuda"):
 # top-B records are all-gathered (B * 16 bytes per rank) and merged identically everywhere.
 # ------------------------------------------------------------------------------------------------
 class ShardedBeamBlock:
-    def __init__(self, D, S, B, omega, max_aux=1024, group=None, device=None):
+    def __init__(self, D, S, B, omega, max_aux=1024, group=None, device=None, single=False):
+        """single=True: ignore an initialised process group and score the whole candidate range on this GPU (the
+        unsharded run a sharded result is compared with)"""
         import torch.distributed as dist
-        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and not single) else None
         self.group = group
         self.rank = self.dist.get_rank(group) if self.dist else 0
         self.world = self.dist.get_world_size(group) if self.dist else 1

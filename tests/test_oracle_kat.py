@@ -86,7 +86,10 @@ def test_is_roundtrip_bit_exact():
 
 
 def test_canonical_score_matches_reference_form():
-    """the centred quadratic (+ dropped constant) equals the reference's two-log_prob form"""
+    """the centred quadratic (+ dropped constant) equals the reference's two-log_prob form: one candidate through the
+    stand-alone reference-form evaluator, then ALL S*B candidates of EVERY partition of several coder-blocks against the
+    exact (float64 throughout) log-ratio at north_star's 1e-5 relative tolerance (tests/test_refform_gap.py holds the
+    population study)."""
     tl, ts, pl, ps = synth.c2(200, data_seed=5)
     r = O.beam_encode_block(tl, ts, pl, ps, 3., 36, 4, 7, trace=True)
     n_aux = r["n_aux"]
@@ -96,7 +99,12 @@ def test_canonical_score_matches_reference_form():
     x = (r["sample"] - pl).astype(np.float32)
     can = r["trace_score"][t, 0] + O.beam_score_constant(tl, ts, pl, ps, n_aux, t)
     ref = O.beam_refform_logw(tl, ts, pl, ps, n_aux, t, x)
-    assert abs(can - ref) <= 1e-4 * max(1.0, abs(ref))
+    assert abs(can - ref) <= 1e-5 * max(1.0, abs(ref))
+    for recipe, D, B, S, seed in (("c2", 200, 4, 36, 7), ("c2", 1000, 20, 36, 42), ("c3", 288, 10, 20, 7), ("c1", 64, 20, 36, 42)):
+        tl, ts, pl, ps = getattr(synth, recipe)(D, data_seed=5)
+        st = O.beam_refform_study(tl, ts, pl, ps, 3., S, B, seed)
+        assert st["tf_partitions"] == st["n_aux"] > 0
+        assert st["max_dev_canon_exact"] <= 1e-5, (recipe, D, st["max_dev_canon_exact"])
 
 
 def test_hash_and_shuffle_helpers():

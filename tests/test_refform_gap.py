@@ -1,0 +1,50 @@
+"""The oracle <-> reference-form gap, quantified (VERDICT r1 "next" item 3).
+
+The coding-path oracle is "parity unpinned" against TensorFlow; what CAN be measured here is how
+the one place where the oracle deliberately departs from the reference's arithmetic -- the canonical log-weight (centred
+quadratic, fixed reduction tree) instead of two float32 `log_prob` passes and an Eigen `reduce_sum`
+(rec/coding/beam_search_coder.py:79-106) -- changes decisions:
+
+* teacher-forced: at every partition of the canonical run, reference-form scores of the SAME beam state; the kept top-B
+  sets must be identical, or differ only between candidates whose reference-form log-weights are within 1e-5 relative;
+* free-running: the reference-form coder on its own state; how many coder-blocks / index positions come out identical;
+* KL: blocks whose float32 (TFP) KL gives another n_aux than the oracle's float64 sum.
+
+Here: 48 coder-blocks of the C2/C3 population (seconds).  The full population (>= 2000 blocks) is
+profiles/r2_refform_study.json, written by `python -m oracle.refform_study --blocks 2048`; its claims are re-checked below.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refform_study as RS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("sum_mode", ["pairwise", "sequential"])
+def test_teacher_forced_and_free_running_small_population(sum_mode):
+    rep = RS.run(24, sum_mode=sum_mode, threads=os.cpu_count())
+    tf, fr = rep["teacher_forced"], rep["free_running"]
+    assert tf["partitions"] > 1500
+    # every teacher-forced kept-set mismatch is a near tie in the reference's own form
+    assert tf["worst_relative_gap_of_a_mismatch"] < 1e-5
+    assert tf["teacher_forced_match_pct"] >= 99.5
+    assert fr["blocks_identical_pct"] >= 90.0
+    assert rep["score_deviation"]["canonical_vs_exact_float64_max"] <= 1e-5
+    # the canonical form is at least as close to the exact log-ratio as the reference's float32 form
+    assert rep["score_deviation"]["canonical_vs_exact_float64_max"] <= rep["score_deviation"]["reference_float32_form_vs_exact_float64_max"]
+
+
+def test_population_record_is_consistent():
+    path = os.path.join(ROOT, "profiles", "r2_refform_study.json")
+    if not os.path.exists(path):
+        pytest.skip("profiles/r2_refform_study.json not generated yet")
+    rep = json.load(open(path))
+    assert rep["blocks"] >= 2000
+    tf = rep["teacher_forced"]
+    assert tf["all_mismatches_within_1e-5"] and tf["worst_relative_gap_of_a_mismatch"] < 1e-5
+    assert tf["kept_set_identical"] + tf["kept_set_mismatches"] == tf["partitions"]
+    assert rep["score_deviation"]["canonical_vs_exact_float64_max"] <= 1e-5
