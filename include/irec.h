@@ -116,7 +116,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
 
 /* Which kernel irec_beam_encode runs for these sizes on the current device (diagnostics, tests, bench reports):
  * 0 = one partition per launch (general path), 1 = k_beam_encode_resident, 2 = k_beam_encode_resident2 (persistent CTA per
- * coder-block), 100 + G = k_beam_encode_cluster with G CTAs per coder-block (few blocks per launch: one image). */
+ * coder-block), 3 = k_beam_encode_tmem (beams and coefficients in tensor memory, two coder-blocks per SM), 100 + G = k_beam_encode_cluster with G CTAs per coder-block (few blocks per launch: one image). */
 int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B);
 
 /* BeamSearchCoder.decode_block over nb blocks (beam_search_coder.py:124-148).  indices

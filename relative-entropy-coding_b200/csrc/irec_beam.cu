@@ -906,13 +906,14 @@ static void launch_resident(const ResidentPlan& p, const ResidentArgs& a, cudaSt
 #define R2_TABLE_MAX_BYTES ((size_t)1 << 30)
 static size_t r2_ws_hist_bytes(int bmax, int max_aux)
 {
-    const size_t h = 512 + sizeof(int2) * (size_t)irec_device().sm_count * (size_t)max_aux * bmax;
+    // 2 x: k_beam_encode_tmem keeps two coder-block contexts per CTA
+    const size_t h = 512 + sizeof(int2) * 2 * (size_t)irec_device().sm_count * (size_t)max_aux * bmax;
     return (h + 255) / 256 * 256;
 }
 static size_t r2_ws_order_bytes(int nb) { return ((size_t)nb * sizeof(int32_t) + 255) / 256 * 256; }
 static size_t r2_ws_sched_bytes()
 {
-    return sizeof(float) * 4 * 1024 * (size_t)irec_device().sm_count;      // [grid][4][DPmax <= 1024]
+    return sizeof(float) * 2 * 4 * 1024 * (size_t)irec_device().sm_count;      // [grid][(2 contexts)][4][DPmax <= 1024]
 }
 // ---- library-owned exponent table, reused across launches (R2TabKey) ----
 #define R2_CACHE_MAX_BYTES ((size_t)256 << 20)
@@ -996,10 +997,12 @@ static size_t r2_table_bytes(int max_D, int S, int max_aux)
 
 static int resident_choice()
 {
-    // IREC_RESIDENT=1 forces the first-generation kernel, =2 the second (tests / A-B runs); default: 2 if it fits
+    // IREC_RESIDENT=1 forces the first-generation kernel, =2 the second, =3 the tensor-memory kernel (tests / A-B runs);
+    // default: 3 where its sizes are covered, else 2 if it fits
     const char* e = getenv("IREC_RESIDENT");
     if (e && e[0] == '1') return 1;
     if (e && e[0] == '2') return 2;
+    if (e && e[0] == '3') return 3;
     return 0;
 }
 
@@ -1435,7 +1438,7 @@ int irec_p2p_exchange(void* const* peer_bufs, int rank, int world, int B, const 
 size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, int B, int max_aux)
 {
     if (irec_init() != IREC_OK) return 0;
-    const int bmax = pick_bmax(B) > 0 ? pick_bmax(B) : 32;
+    const int bmax = B <= 1 ? 1 : (B <= 10 ? 10 : (B <= 20 ? 20 : 32));     // the largest beam capacity any persistent kernel picks for B
     const size_t resident = r2_ws_hist_bytes(bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb) +
                             r2_table_bytes((int)max_block_dim, S, max_aux);
     const size_t general = (state_bytes((int)max_block_dim, B, max_aux) + 255) / 256 * 256 + sizeof(irec_record_t) * 32 + 256 +
@@ -1454,8 +1457,9 @@ int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B)
         const int G = irec_cluster_choice(nb, (int)max_block_dim, S, B);
         if (G > 0) return 100 + G;
     }
-    if (rchoice != 1 && plan_resident2(nb, (int)max_block_dim, S, B).ok) return 2;
-    if (rchoice != 2 && plan_resident(nb, (int)max_block_dim, S, B).ok) return 1;
+    if ((rchoice == 0 || rchoice == 3) && irec_tmem_plan(nb, (int)max_block_dim, S, B, nullptr)) return 3;
+    if (rchoice != 1 && rchoice != 3 && plan_resident2(nb, (int)max_block_dim, S, B).ok) return 2;
+    if (rchoice != 2 && rchoice != 3 && plan_resident(nb, (int)max_block_dim, S, B).ok) return 1;
     return 0;
 }
 
@@ -1503,7 +1507,37 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
                                    S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
                                    nullptr, tab, max_aux, s);
     }
-    if (!irec_force_general() && rchoice != 1) {
+    if (!irec_force_general() && (rchoice == 0 || rchoice == 3)) {
+        TmemPlan tp;
+        if (irec_tmem_plan(nb, (int)max_block_dim, S, B, &tp)) {
+            // tensor-memory kernel (irec_tmem.cu); same workspace layout as resident2
+            int* counter = reinterpret_cast<int*>(workspace);
+            if (cudaMemsetAsync(counter, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+            unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+            int2* hist = reinterpret_cast<int2*>(w + 512);
+            float* sched = reinterpret_cast<float*>(w + r2_ws_hist_bytes(tp.bmax, max_aux));
+            R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
+            int32_t* order = reinterpret_cast<int32_t*>(w + r2_ws_hist_bytes(tp.bmax, max_aux) + r2_ws_sched_bytes());
+            if (cudaMemsetAsync(dplan, 0, sizeof(R2Plan), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");
+            k_r2_plan<<<1, 1024, 0, s>>>(block_offsets, nb, dplan, order);
+            irec_count_launch();
+            const size_t tab_bytes = r2_table_bytes((int)max_block_dim, S, max_aux);
+            if (tab_bytes && !r2_no_table()) {
+                uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(tp.bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb));
+                const R2TabUse u = r2_tab_acquire(tab, seed, S, max_aux, tp.DPmax >> 2, s);
+                r2_build_table(u, dplan, seed, S, max_aux, tp.DPmax >> 2, s);
+                const int rc = irec_launch_tmem(tp, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, S, B, seed,
+                                                out_indices, max_aux, out_n_aux, out_status, out_sample, hist, sched, counter, order,
+                                                dplan, u.tab, u.tab_aux, s);
+                r2_tab_release(u, s);
+                return rc;
+            }
+            return irec_launch_tmem(tp, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, S, B, seed, out_indices,
+                                    max_aux, out_n_aux, out_status, out_sample, hist, sched, counter, order, nullptr, nullptr, max_aux, s);
+        }
+        if (rchoice == 3) return irec_fail(IREC_E_CAPACITY, "beam_encode: IREC_RESIDENT=3 but the sizes do not fit the tensor-memory kernel");
+    }
+    if (!irec_force_general() && rchoice != 1 && rchoice != 3) {
         const ResidentPlan plan2 = plan_resident2(nb, (int)max_block_dim, S, B);
         if (plan2.ok) {
             int* counter = reinterpret_cast<int*>(workspace);
@@ -1542,7 +1576,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
         }
         if (rchoice == 2) return irec_fail(IREC_E_CAPACITY, "beam_encode: IREC_RESIDENT=2 but the sizes do not fit the resident2 kernel");
     }
-    const ResidentPlan plan = irec_force_general() ? ResidentPlan{} : plan_resident(nb, (int)max_block_dim, S, B);
+    const ResidentPlan plan = (irec_force_general() || rchoice == 3) ? ResidentPlan{} : plan_resident(nb, (int)max_block_dim, S, B);
     if (plan.ok) {
         int* counter = reinterpret_cast<int*>(workspace);
         if (cudaMemsetAsync(counter, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode: memset failed");

@@ -220,18 +220,34 @@ __device__ __forceinline__ int n_aux_from_kl(float kl, float omega)
     return (int)ceilf(q);
 }
 
-// canonical tree over nch chunk sums in shared memory (all threads call)
-__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch)
+// Who takes part in a CTA-level helper: the whole CTA (default), or a group of whole warps that synchronises on its own
+// named barrier (the two coder-block contexts of k_beam_encode_tmem, irec_tmem.cu).
+struct CtaGroup {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nt() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct WarpGroup {
+    int t, n, bar;                 // thread index inside the group, group size (multiple of 32), barrier id (1..15)
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ int nt() const { return n; }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
+};
+
+// canonical tree over nch chunk sums in shared memory (all threads of the group call)
+template <class Group>
+__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch, const Group& grp)
 {
     const int P = next_pow2_int(nch);
-    __syncthreads();
+    grp.sync();
     for (int stride = 1; stride < P; stride <<= 1) {
-        for (int i = threadIdx.x * 2 * stride; i + stride < nch; i += blockDim.x * 2 * stride)
+        for (int i = grp.tid() * 2 * stride; i + stride < nch; i += grp.nt() * 2 * stride)
             cs[i] = __dadd_rn(cs[i], cs[i + stride]);
-        __syncthreads();
+        grp.sync();
     }
     return cs[0];
 }
+__device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch) { return block_tree_sum_f64(cs, nch, CtaGroup{}); }
 
 // ---------------------------------------------------------------------------------------------
 // block_topk: out[0..Kout) = the Kout = min(K, n) best of n candidates, best first, by
@@ -239,10 +255,11 @@ __device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch)
 // Scratch (shared): s_gmax [>= blockDim.x floats], s_list [cap ints], s_ctl [4 ints/floats].
 // All threads of the CTA must call it.  NaN scores must have been mapped to -inf by the caller.
 // ---------------------------------------------------------------------------------------------
+template <class Group>
 __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, int n, int K, float* out_sc,
-                                          int32_t* out_id, float* s_gmax, int32_t* s_list, int cap, int32_t* s_ctl)
+                                          int32_t* out_id, float* s_gmax, int32_t* s_list, int cap, int32_t* s_ctl, const Group& grp)
 {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = grp.tid(), nt = grp.nt();
     const int Kout = K < n ? K : n;
     if (Kout <= 0) return 0;
     const float NEG_INF = __int_as_float(0xff800000);
@@ -259,7 +276,7 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
         for (int stride = gsz >> 1; stride >= 1; stride >>= 1)
             lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, stride));
         if ((tid & (gsz - 1)) == 0) s_gmax[tid / gsz] = lmax;
-        __syncthreads();
+        grp.sync();
         const int G = nt / gsz;
         if (tid < G) {
             const float mine = s_gmax[tid];
@@ -271,7 +288,7 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
             if (cnt == Kout - 1) s_ctl[1] = __float_as_int(mine);
         }
     }
-    __syncthreads();
+    grp.sync();
     const float tau = __int_as_float(s_ctl[1]);
 
     // 2. survivors
@@ -281,7 +298,7 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
             if (pos < cap) s_list[pos] = i;
         }
     }
-    __syncthreads();
+    grp.sync();
     const int ns = s_ctl[0];
 
     if (ns <= cap) {
@@ -299,7 +316,7 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
             }
             if (rank < Kout) { out_sc[rank] = v; out_id[rank] = f; }
         }
-        __syncthreads();
+        grp.sync();
     } else {
         // 4. fallback (massive ties): Kout rounds of CTA-wide arg-best with exclusion of the
         //    already selected (everything strictly better than the previous pick is selected)
@@ -320,7 +337,7 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
                 if ((ov > bv) || (ov == bv && of < bf)) { bv = ov; bf = of; }
             }
             if ((tid & 31) == 0) { s_gmax[tid >> 5] = bv; s_list[tid >> 5] = bf; }
-            __syncthreads();
+            grp.sync();
             if (tid == 0) {
                 for (int w = 1; w < (nt >> 5); ++w) {
                     const float ov = s_gmax[w];
@@ -329,10 +346,15 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
                 }
                 out_sc[k] = bv; out_id[k] = bf;
             }
-            __syncthreads();
+            grp.sync();
             prev_v = out_sc[k]; prev_f = out_id[k];
-            __syncthreads();
+            grp.sync();
         }
     }
     return Kout;
+}
+__device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, int n, int K, float* out_sc,
+                                          int32_t* out_id, float* s_gmax, int32_t* s_list, int cap, int32_t* s_ctl)
+{
+    return block_topk(sc, id, n, K, out_sc, out_id, s_gmax, s_list, cap, s_ctl, CtaGroup{});
 }

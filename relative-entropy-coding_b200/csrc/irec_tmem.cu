@@ -1,0 +1,584 @@
+// irec_tmem.cu -- K1a third generation: k_beam_encode_tmem, the persistent beam-search encoder with the beams and the
+// per-dim coefficients in TENSOR MEMORY and two coder-blocks in flight per SM.
+//
+// Reference loop being replaced: rec/coding/beam_search_coder.py:53-122 (one context = one coder-block, all of its auxiliary
+// variables); results are bit-identical to k_beam_encode_resident2, k_beam_encode_resident and the oracle.
+//
+// Why (profiles/r1_resident2_e_bench_launch_ncu.md, profiles/r2_tmem_probe.log): resident2 is bound by the shared-memory
+// data pipe -- 2.15 wavefronts per quantile gather plus one LDS.128 per beam quad and four per coefficient quad (18 % of
+// the wavefronts) -- and leaves the SM idle in the serial phases between scoring passes (top-B, re-materialisation, next
+// schedule: 22 % of the time); a second coder-block per SM would hide those, but two 80 KB beam matrices do not fit beside
+// the 120 KB quantile table.  Both problems have one cause: data that is LANE-PRIVATE and indexed WARP-UNIFORMLY (lane l
+// owns the 32-dim chunk l; every lane of a warp reads "beam b, quad iq" of its own chunk) sits in shared memory.  That
+// access pattern is exactly what tensor memory offers through tcgen05.ld/st.32x32b: thread i of warp w addresses TMEM lane
+// 32 (w % 4) + i, columns are addressed warp-uniformly, 512 columns x 128 lanes x 4 B = 256 KB per SM that this path never
+// used -- and tcgen05.ld runs beside a saturated shared-memory pipe at no cost (measured: 1653 cycles per 480 conflicted
+// gathers with or without 14 tcgen05.ld.x4 per 40 gathers).
+//
+// Layout.  12 warps; warp w belongs to context c = (w >> 1) & 1, beam half h = w & 1, and is warp wi = w >> 2 of the three
+// warps of its TMEM lane quarter q = w & 3 = 2 c + h.  Quarter q, lane (row r, chunk l), holds
+//   columns [0, 32 HB)            the HB = BMAX / 2 beams of half h: beam lb, dim 32 l + i  at column 32 lb + i
+//   columns [32 HB, 32 HB + 128)  the coefficients of chunk l: sigma_aux, A, E, M, 32 columns each
+// so a context owns two quarters (one per beam half), the two contexts the whole 512-column allocation, and nothing is
+// replicated.  Shared memory keeps the quantile table (shared by both contexts), per context the scores / top-B scratch and
+// one 40 KB staging buffer through which re-materialised beams and new coefficients reach the quarters that hold them.
+// The contexts synchronise on named barriers (bar.sync 1 + c, 192 threads) and draw coder-blocks from the same queue; while
+// one runs its serial phases the other one scores.
+#define IREC_R2_DEVICE_ONLY
+#include "irec_resident2.cuh"
+#include "irec_host.h"
+
+#define TM_THREADS 384
+#define TM_CTX_THREADS 192
+#define TM_WARPS_PER_QUARTER 3
+#define TM_COLS 512
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 wrappers (PTX ISA: tcgen05.alloc/dealloc/ld/st/wait/fence).  All .sync.aligned: every lane of the warp executes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tm_alloc(uint32_t* slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem_u32(slot)), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TM_COLS) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, float (&r)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const float4 v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const float4 a, const float4 b, const float4 c, const float4 d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w),
+                   "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w) : "memory");
+}
+// tcgen05.wait::ld with the loaded registers as in/out operands: nothing that uses them can be scheduled above the wait
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_tie4(float (&r)[4]) { asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3])); }
+__device__ __forceinline__ void tm_tie16(float (&r)[16])
+{
+    asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                      "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk sums of NS candidate samples against the HB beams of this warp's half.  Same float32 operation order per
+// candidate-dim as r2_score_chunk / the oracle (beam_score):  x = beam + T2[a + c_b] * sigma_aux;  d = x - M;
+// acc = fma(fma(A, d, E), d, acc).   tm_beams / tm_coef: TMEM addresses (quarter lane base + first column).
+// ---------------------------------------------------------------------------------------------
+//   TAB: exponents from the launch table (row[k] = uint2 index of sample k's row + chunk); otherwise from Philox + dl4 in place
+//   (j_base[k] = s_k * D + first dim of the chunk) with the one-shot bank spreading of the general path.
+template <int HB, int NS, bool TAB>
+__device__ __forceinline__ void tm_score_chunk(const char* __restrict__ T2b, uint32_t tm_beams, uint32_t tm_coef,
+                                               const uint32_t (&cb)[HB], int P, const uint2* __restrict__ tab_t,
+                                               const uint32_t (&row)[NS], const uint16_t* __restrict__ dl4, const TfStream& st,
+                                               const uint64_t (&j_base)[NS], float (&acc)[NS][HB])
+{
+    constexpr int G = R2Group<HB>::G;
+    uint2 nxt[NS];
+    if (TAB) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) nxt[k] = __ldg(tab_t + row[k]);
+    }
+#pragma unroll 1
+    for (int iq = 0; iq < 8; ++iq) {
+        uint32_t ad[NS][4];
+        if (TAB) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) r2_unpack(nxt[k], ad[k][0], ad[k][1], ad[k][2], ad[k][3]);
+            if (iq < 7) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) nxt[k] = __ldg(tab_t + row[k] + (iq + 1) * P);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const uint64_t j = j_base[k] + 4 * iq;
+                const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
+                ad[k][0] = r2_spread_banks(r2_exp4(dl4, u.x)); ad[k][1] = r2_spread_banks(r2_exp4(dl4, u.y));
+                ad[k][2] = r2_spread_banks(r2_exp4(dl4, u.z)); ad[k][3] = r2_spread_banks(r2_exp4(dl4, u.w));
+            }
+        }
+        float sa[4], A[4], E[4], M[4];
+        tm_ld4(tm_coef + 4 * iq, sa);
+        tm_ld4(tm_coef + 32 + 4 * iq, A);
+        tm_ld4(tm_coef + 64 + 4 * iq, E);
+        tm_ld4(tm_coef + 96 + 4 * iq, M);
+        float bm[HB][4];
+#pragma unroll
+        for (int b = 0; b < HB; ++b) tm_ld4(tm_beams + 32 * b + 4 * iq, bm[b]);
+        tm_wait_ld();
+        tm_tie4(sa); tm_tie4(A); tm_tie4(E); tm_tie4(M);
+#pragma unroll
+        for (int b = 0; b < HB; ++b) tm_tie4(bm[b]);
+#pragma unroll
+        for (int b0 = 0; b0 < HB; b0 += G) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                float tv[G][4];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        tv[g][e] = *reinterpret_cast<const float*>(T2b + (ad[k][e] + cb[b0 + g]));
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float a = acc[k][b0 + g];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float x = __fadd_rn(bm[b0 + g][e], __fmul_rn(tv[g][e], sa[e]));
+                        const float d = __fadd_rn(x, -M[e]);
+                        const float t = __fmaf_rn(A[e], d, E[e]);
+                        a = __fmaf_rn(t, d, a);
+                    }
+                    acc[k][b0 + g] = a;
+                }
+            }
+        }
+    }
+}
+
+// one round of a warp: NS sample groups against the HB beams [boff, boff + HB) of its half -> s_scores
+struct TmSrc {             // where the exponents of a partition come from
+    const uint2* tab_t;     // launch table of this block size and auxiliary variable, or nullptr
+    int row_stride;
+    const uint16_t* dl4;
+    TfStream st;
+};
+
+template <int HB, int NS, bool TAB>
+__device__ __forceinline__ void tm_score_round(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const uint32_t* s_cb,
+                                               const BeamGeom& g, int lane, const TmSrc& src, int sg_first,
+                                               int sg_stride, int S, int Bcur, int boff, float* s_scores)
+{
+    const int lg = lane & (g.P - 1);
+    uint32_t row[NS];
+    uint64_t jb[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int sk = (sg_first + k * sg_stride) * g.SPW + lane / g.P;
+        const int sc = min(sk, S - 1);
+        row[k] = (uint32_t)(sc * src.row_stride + lg);
+        jb[k] = TAB ? 0ull : (uint64_t)sc * (uint64_t)g.D + (uint64_t)(32 * lg);
+    }
+    uint32_t cb[HB];
+#pragma unroll
+    for (int b = 0; b < HB; ++b) cb[b] = s_cb[boff + b];
+    float acc[NS][HB];
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
+    tm_score_chunk<HB, NS, TAB>(T2b, tm_beams, tm_coef, cb, g.P, src.tab_t, row, src.dl4, src.st, jb, acc);
+    float v[NS * HB];
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
+    const R2LocalSink sink{ s_scores, S, Bcur, boff };
+    r2_tree_store<NS * HB, NS * HB, HB, 0, R2LocalSink>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, sink);
+}
+
+// all candidates of one partition that belong to this warp: the sample groups wi, wi + 3, ... against its beam half
+template <int HB, bool TAB>
+__device__ __forceinline__ void tm_score_partition(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const uint32_t* s_cb,
+                                                   const BeamGeom& g, int lane, int wi, const TmSrc& src, int S,
+                                                   int Bcur, int boff, float* s_scores)
+{
+    constexpr int NW = TM_WARPS_PER_QUARTER;
+    const int nsg = (S + g.SPW - 1) / g.SPW;
+    int sg = 0;
+    // rounds of 3, then 2, then 1 sample groups per warp (all warps of the quarter take the same branch)
+    while (nsg - sg > 2 * NW) {
+        if (sg + wi < nsg)   // groups beyond nsg are clamped inside (scores not stored)
+            tm_score_round<HB, 3, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        sg += 3 * NW;
+    }
+    if (nsg - sg > NW) {
+        if (sg + wi < nsg)
+            tm_score_round<HB, 2, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        sg += 2 * NW;
+    } else if (nsg - sg > 0) {
+        if (sg + wi < nsg)
+            tm_score_round<HB, 1, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        sg += NW;
+    }
+}
+
+struct TmemArgs {
+    const float* t_loc; const float* t_scale; const float* p_loc; const float* p_scale;
+    const int64_t* gidx; const int64_t* offs; int nb;
+    float omega; int S; int B; int64_t seed;
+    int32_t* out_indices; int max_aux; int32_t* out_n_aux; int32_t* out_status; float* out_sample;
+    const float* T2; const uint16_t* dl4; const float* ratio_tab; int ratio_len;
+    int2* hist;            // [2 * gridDim.x][max_aux][BMAX]
+    int* work_counter;     // dynamic block queue
+    int DPmax;             // padded dims capacity (multiple of 32, <= 1024)
+    int NC;                // capacity of a context's score array (>= S * BMAX)
+    float* sched;          // [2 * gridDim.x][4][DPmax] per-context scratch: sigma_p^2, sigma_t^2, delta mu, cumulative variance
+    const int32_t* order;  // queue position -> coder-block (largest blocks first), or nullptr
+    const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
+    const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
+    int tab_aux;
+};
+
+template <int BMAX>
+__host__ __device__ constexpr size_t tm_stage_floats(int DPmax)
+{
+    return (size_t)(BMAX * (DPmax / 2) > 4 * DPmax ? BMAX * (DPmax / 2) : 4 * DPmax);
+}
+template <int BMAX>
+__host__ __device__ constexpr size_t tm_ctx_bytes(int DPmax, int NC)
+{
+    return 32 * sizeof(double) + sizeof(float) * ((size_t)NC + 256 + 32 + tm_stage_floats<BMAX>(DPmax)) +
+           sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32);
+}
+template <int BMAX>
+__host__ __device__ constexpr size_t tm_smem_bytes(int DPmax, int NC)
+{
+    return sizeof(float) * (size_t)IREC_T2_LEN + 2 * tm_ctx_bytes<BMAX>(DPmax, NC) + 16;
+}
+
+template <int BMAX>
+__global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemArgs a)
+{
+    static_assert(BMAX % 2 == 0 && BMAX * 16 + 128 <= TM_COLS, "beam half + coefficients must fit the 512 TMEM columns");
+    constexpr int HB = BMAX / 2;
+    constexpr uint32_t COEF0 = 32u * HB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tmem_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (warp >> 1) & 1, h = warp & 1, wi = warp >> 2;
+    const int DPm = a.DPmax;
+    const WarpGroup grp{ (2 * wi + h) * 32 + lane, TM_CTX_THREADS, 1 + c };
+    const int tid = grp.tid();
+    constexpr int nt = TM_CTX_THREADS;
+
+    // ---- shared memory carve-up ----
+    float* s_T2 = reinterpret_cast<float*>(smem_raw);                                    // [IREC_T2_LEN], both contexts
+    unsigned char* cbase = smem_raw + sizeof(float) * (size_t)IREC_T2_LEN + (size_t)c * tm_ctx_bytes<BMAX>(DPm, a.NC);
+    double* s_kl = reinterpret_cast<double*>(cbase);                                     // [32]
+    float* s_scores = reinterpret_cast<float*>(s_kl + 32);                               // [NC]
+    float* s_gmax = s_scores + a.NC;                                                     // [256]
+    float* s_wsc = s_gmax + 256;                                                         // [32] winners' scores
+    float* s_stage = s_wsc + 32;                                                         // staging: beams [BMAX][4][P] float4 / coefficients [4][DP]
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_stage + tm_stage_floats<BMAX>(DPm));   // [32] winners' flat ids
+    int32_t* s_list = s_wid + 32;                                                        // [R2_TOPK_CAP]
+    int32_t* s_ctl = s_list + R2_TOPK_CAP;                                               // [4]
+    int32_t* s_hsum = s_ctl + 4;                                                         // [2][32]
+    int32_t* s_misc = s_hsum + 64;                                                       // [4]
+    uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_misc + 4);                            // [32] 4 * dlog(h_b)
+    float4* stage4 = reinterpret_cast<float4*>(s_stage);
+
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.T2);
+        float4* dst = reinterpret_cast<float4*>(s_T2);
+        for (int i = threadIdx.x; i < IREC_T2_LEN / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    if (warp == 0) tm_alloc(&s_tmem_base);
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t tm_q = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);            // this warp's lane quarter
+    const uint32_t tm_coef = tm_q + COEF0;
+    const char* T2b = reinterpret_cast<const char*>(s_T2);
+    const int slot = 2 * blockIdx.x + c;
+    int2* hist = a.hist + (size_t)slot * a.max_aux * BMAX;
+    float* g_cv = a.sched + (size_t)slot * 4 * DPm;                                      // global scratch (this context only), CI layout
+    float* g_tv = g_cv + DPm; float* g_dmu = g_tv + DPm; float* g_cum = g_dmu + DPm;
+    const int row_stride = DPm >> 2;
+
+    auto ctx_sync = [&]() { tm_fence_before(); grp.sync(); tm_fence_after(); };
+
+    // Block queue: context 0 of every CTA starts with queue position blockIdx.x, everything else is drawn dynamically from
+    // gridDim.x on -- no CTA holds two coder-blocks before every CTA holds one.
+    bool first = (c == 0);
+    for (;;) {
+        ctx_sync();
+        if (tid == 0) s_misc[0] = first ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.work_counter, 1);
+        first = false;
+        ctx_sync();
+        if (s_misc[0] >= a.nb) break;
+        const int blk = a.order ? a.order[s_misc[0]] : s_misc[0];
+        const int64_t off = a.offs[blk];
+        const int D = (int)(a.offs[blk + 1] - off);
+        const BeamGeom g = make_geom(D);
+        const int lg = lane & (g.P - 1);
+        const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
+        if (a.tab) {
+#pragma unroll
+            for (int k = 0; k < R2_MAX_SIZES; ++k)
+                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
+        }
+
+        // ---- load + KL (coder.py:499-501) ----
+        for (int i = tid; i < g.DP; i += nt) { g_cv[i] = 0.f; g_tv[i] = 0.f; g_dmu[i] = 0.f; g_cum[i] = 0.f; }
+        {   // the beams of this quarter start at zero (t = 0 scores the single empty beam; slots >= Bcur are never read back)
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int lb = wi; lb < HB; lb += TM_WARPS_PER_QUARTER) {
+                tm_st16(tm_q + 32 * lb, z, z, z, z);
+                tm_st16(tm_q + 32 * lb + 16, z, z, z, z);
+            }
+        }
+        ctx_sync();
+        for (int ch = tid; ch < g.nch; ch += nt) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * ch + 32);
+            for (int d = 32 * ch; d < hi; ++d) {
+                const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
+                acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
+                const int ci = ci_index(d, g.P);
+                g_cv[ci] = __fmul_rn(ps, ps);
+                g_tv[ci] = __fmul_rn(ts, ts);
+                g_dmu[ci] = __fadd_rn(tl, -pl);
+            }
+            s_kl[ch] = acc;
+        }
+        const double kld = block_tree_sum_f64(s_kl, g.nch, grp);
+        const int n_aux = n_aux_from_kl((float)kld, a.omega);
+        int status = IREC_BLK_OK;
+        if (n_aux <= 0) status = IREC_BLK_BAD_KL;
+        else if (n_aux > a.max_aux || n_aux > a.ratio_len) status = IREC_BLK_TOO_LONG;
+        if (tid == 0) { a.out_n_aux[blk] = n_aux; a.out_status[blk] = status; }
+        if (status != IREC_BLK_OK) continue;
+
+        if (tid < 64) s_hsum[tid] = 0;
+        int Bcur = 1, hb = 0;                      // hb: which half of s_hsum is current
+
+        // Coefficients of auxiliary variable t (beam_search_coder.py:64-77): every thread computes its dims into the staging
+        // buffer (CI layout, zeros in the padding), then each quarter copies all four arrays into its TMEM columns.
+        auto schedule_to_tmem = [&](float ratio, const int32_t* hs_new, int Knew) {
+            for (int i = tid; i < g.DP; i += nt) {
+                SchedOut o;
+                o.sa = 0.f; o.A = 0.f; o.E = 0.f; o.M = 0.f; o.cum_next = 0.f;
+                const float cv = g_cv[i];
+                if (cv != 0.f) {
+                    o = beam_sched_dim(cv, g_tv[i], g_dmu[i], g_cum[i], ratio);
+                    g_cum[i] = o.cum_next;
+                }
+                s_stage[i] = o.sa; s_stage[DPm + i] = o.A; s_stage[2 * DPm + i] = o.E; s_stage[3 * DPm + i] = o.M;
+            }
+            if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
+            ctx_sync();
+            for (int pr = wi; pr < 32; pr += TM_WARPS_PER_QUARTER) {          // (array, quad) pairs of this quarter
+                const int arr = pr >> 3, iq = pr & 7;
+                tm_st4(tm_coef + 32 * arr + 4 * iq, stage4[arr * (DPm >> 2) + iq * g.P + lg]);
+            }
+            tm_wait_st();
+            ctx_sync();
+        };
+        schedule_to_tmem(a.ratio_tab[n_aux - 1], s_hsum, 1);      // empty index row: hash sum 0
+
+        for (int t = 0; t < n_aux; ++t) {
+            const int32_t* hs = s_hsum + 32 * hb;
+            TmSrc src;
+            src.tab_t = tab_blk ? tab_blk + (size_t)t * a.S * row_stride : nullptr;
+            src.row_stride = row_stride; src.dl4 = a.dl4; src.st = tf_stream_seeded(a.seed + t, a.seed + t);
+
+            // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102): this warp's beam half ----
+            if (src.tab_t) {
+                if (Bcur == 1) {
+                    if (h == 0) tm_score_partition<1, true>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, 1, 0, s_scores);
+                } else if (h * HB < Bcur) {
+                    tm_score_partition<HB, true>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, Bcur, h * HB, s_scores);
+                }
+            } else {
+                if (Bcur == 1) {
+                    if (h == 0) tm_score_partition<1, false>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, 1, 0, s_scores);
+                } else if (h * HB < Bcur) {
+                    tm_score_partition<HB, false>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, Bcur, h * HB, s_scores);
+                }
+            }
+            ctx_sync();
+
+            // ---- top-B (beam_search_coder.py:86-89,104-106) ----
+            const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl, grp);
+
+            // ---- history + hash sums of the new beams (:92-95); (s_j, b_j) for the re-materialisation ----
+            int32_t* hs_new = s_hsum + 32 * (hb ^ 1);
+            if (tid < Kout) {
+                const int f = s_wid[tid];
+                const int sj = f / Bcur, bj = f - sj * Bcur;
+                hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
+                hs_new[tid] = hsum_extend(hs[bj], sj, t);
+                s_list[tid] = sj; s_list[32 + tid] = bj;
+            }
+            ctx_sync();
+
+            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93), 16 dims of every chunk per round.
+            //      A winner is computed by a warp of the quarter that holds its PARENT (lane = chunk), staged in shared memory,
+            //      and copied into the quarter that holds its new slot; all parents of a round are read before any slot is written.
+            for (int rd = 0; rd < 2; ++rd) {
+                int mine = 0;
+                for (int j = 0; j < Kout; ++j) {
+                    const int bj = s_list[32 + j];
+                    if (bj / HB != h) continue;                       // parent lives in the other half (warp-uniform)
+                    if ((mine++) % TM_WARPS_PER_QUARTER != wi) continue;
+                    const int sj = s_list[j], lb = bj - h * HB;
+                    uint2 ex[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (src.tab_t) {
+                            ex[q] = __ldg(src.tab_t + (size_t)sj * row_stride + (4 * rd + q) * g.P + lg);
+                        } else {                                      // 4 x uint16 word offsets, as the table stores them
+                            const int d0 = 32 * lg + 4 * (4 * rd + q);
+                            ex[q] = make_uint2(0u, 0u);
+                            if (d0 < D) {
+                                const uint4 u = tf_stream_quad_at(src.st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                                const uint32_t w0 = r2_exp4(a.dl4, u.x) >> 2, w1 = d0 + 1 < D ? r2_exp4(a.dl4, u.y) >> 2 : 0u;
+                                const uint32_t w2 = d0 + 2 < D ? r2_exp4(a.dl4, u.z) >> 2 : 0u, w3 = d0 + 3 < D ? r2_exp4(a.dl4, u.w) >> 2 : 0u;
+                                ex[q] = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+                            }
+                        }
+                    }
+                    float par[16], sa[16];
+                    tm_ld16(tm_q + 32 * lb + 16 * rd, par);
+                    tm_ld16(tm_coef + 16 * rd, sa);
+                    tm_wait_ld();
+                    tm_tie16(par); tm_tie16(sa);
+                    const uint32_t cb = s_cb[bj];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t e0, e1, e2, e3;
+                        r2_unpack(ex[q], e0, e1, e2, e3);
+                        float4 o;
+                        o.x = __fadd_rn(par[4 * q + 0], __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa[4 * q + 0]));
+                        o.y = __fadd_rn(par[4 * q + 1], __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa[4 * q + 1]));
+                        o.z = __fadd_rn(par[4 * q + 2], __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa[4 * q + 2]));
+                        o.w = __fadd_rn(par[4 * q + 3], __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa[4 * q + 3]));
+                        // padding dims: sigma_aux = 0 and the parent is 0 there, so the padding stays zero
+                        if (lane < g.P) stage4[(j * 4 + q) * g.P + lg] = o;
+                    }
+                }
+                ctx_sync();
+                for (int lb = wi; lb < HB; lb += TM_WARPS_PER_QUARTER) {
+                    const int j = h * HB + lb;
+                    if (j < Kout)
+                        tm_st16(tm_q + 32 * lb + 16 * rd, stage4[(j * 4 + 0) * g.P + lg], stage4[(j * 4 + 1) * g.P + lg],
+                                stage4[(j * 4 + 2) * g.P + lg], stage4[(j * 4 + 3) * g.P + lg]);
+                }
+                tm_wait_st();
+                ctx_sync();
+            }
+
+            // ---- coefficients and table offsets c_b of the next auxiliary variable ----
+            if (t + 1 < n_aux) schedule_to_tmem(a.ratio_tab[n_aux - 2 - t], hs_new, Kout);
+            Bcur = Kout;
+            hb ^= 1;
+        }
+
+        // ---- emit: indices of the best beam (trace the back-pointers) and its sample (:118-122) ----
+        if (tid == 0) {
+            int j = 0;
+            int32_t* oi = a.out_indices + (size_t)blk * a.max_aux;
+            for (int t = n_aux - 1; t >= 0; --t) {
+                const int2 e = hist[(size_t)t * BMAX + j];
+                oi[t] = e.x;
+                j = e.y;
+            }
+        }
+        if (h == 0) {                              // beam 0 lives in the first quarter of the context
+            for (int iq = wi; iq < 8; iq += TM_WARPS_PER_QUARTER) {
+                float b0[4];
+                tm_ld4(tm_q + 4 * iq, b0);
+                tm_wait_ld();
+                tm_tie4(b0);
+                if (lane < g.P) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int d = 32 * lg + 4 * iq + e;
+                        if (d < D) {
+                            const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                            a.out_sample[gi] = __fadd_rn(b0[e], a.p_loc[gi]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    if (warp == 0) tm_dealloc(s_tmem_base);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int tm_pick_bmax(int B)
+{
+    if (B > 1 && B <= 10) return 10;
+    if (B > 10 && B <= 20) return 20;
+    return -1;                                     // B = 1 and B > 20: the resident2 / resident kernels
+}
+
+template <int BMAX>
+static bool tm_plan_t(int max_D, int S, TmemPlan& p)
+{
+    if (max_D > 1024 || max_D < 1 || (int64_t)S * BMAX > 32768 || (int64_t)S * BMAX > R2_TOPK_CAP * 16) return false;
+    const BeamGeom g = make_geom(max_D);
+    p.bmax = BMAX; p.DPmax = g.DP; p.NC = ((S * BMAX + 31) / 32) * 32;
+    p.smem = tm_smem_bytes<BMAX>(p.DPmax, p.NC);
+    if (p.smem > (size_t)irec_device().max_smem_optin) return false;
+    return cudaFuncSetAttribute(k_beam_encode_tmem<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+}
+
+bool irec_tmem_plan(int nb, int max_D, int S, int B, TmemPlan* out)
+{
+    TmemPlan p{};
+    bool ok = false;
+    switch (tm_pick_bmax(B)) {
+        case 10: ok = tm_plan_t<10>(max_D, S, p); break;
+        case 20: ok = tm_plan_t<20>(max_D, S, p); break;
+        default: ok = false;
+    }
+    if (!ok) return false;
+    p.grid = std::max(1, std::min(nb, irec_device().sm_count));     // two contexts per CTA; see the queue policy in the kernel
+    if (out) *out = p;
+    return true;
+}
+
+int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                     const int64_t* gidx, const int64_t* offs, int nb, float omega, int S, int B, int64_t seed,
+                     int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
+                     int2* hist, float* sched, int* work_counter, const int32_t* order, const void* plan, const void* tab, int tab_aux,
+                     cudaStream_t s)
+{
+    TmemArgs a;
+    a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
+    a.gidx = gidx; a.offs = offs; a.nb = nb; a.omega = omega; a.S = S; a.B = B; a.seed = seed;
+    a.out_indices = out_indices; a.max_aux = max_aux; a.out_n_aux = out_n_aux; a.out_status = out_status;
+    a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
+    a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
+    a.hist = hist; a.work_counter = work_counter; a.DPmax = p.DPmax; a.NC = p.NC; a.sched = sched; a.order = order;
+    a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux;
+    switch (p.bmax) {
+        case 10: k_beam_encode_tmem<10><<<p.grid, TM_THREADS, p.smem, s>>>(a); break;
+        case 20: k_beam_encode_tmem<20><<<p.grid, TM_THREADS, p.smem, s>>>(a); break;
+        default: return irec_fail(IREC_E_INVALID, "irec_launch_tmem: unsupported beam capacity");
+    }
+    irec_count_launch();
+    return irec_check_launch("k_beam_encode_tmem");
+}

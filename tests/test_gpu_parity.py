@@ -110,6 +110,8 @@ KERNEL_ENV = {
     "resident1": {"IREC_RESIDENT": "1"},                              # k_beam_encode_resident
     "resident2": {"IREC_RESIDENT": "2"},                              # k_beam_encode_resident2 (discrete-log table addressing)
     "resident2-notable": {"IREC_RESIDENT": "2", "IREC_R2_NO_TABLE": "1"},   # exponents from Philox + dlog in place
+    "tmem": {"IREC_RESIDENT": "3"},                                   # k_beam_encode_tmem (beams in tensor memory, two contexts per SM)
+    "tmem-notable": {"IREC_RESIDENT": "3", "IREC_R2_NO_TABLE": "1"},
     "cluster8": {"IREC_CLUSTER": "8"},                                # k_beam_encode_cluster, 8 CTAs per coder-block
     "cluster4": {"IREC_CLUSTER": "4"},
     "cluster8-notable": {"IREC_CLUSTER": "8", "IREC_R2_NO_TABLE": "1"},
@@ -135,11 +137,13 @@ class kernel_env:
 def test_beam_resident_vs_oracle(cuda, case, kernel):
     """both generations of the persistent per-block kernel and the cluster-per-block kernel (with and without the
     per-launch exponent table) are bit-identical to the oracle"""
+    if kernel.startswith("tmem") and not 2 <= case[5] <= 20:
+        pytest.skip("k_beam_encode_tmem covers 2 <= n_beams <= 20 (others run resident2)")
     with kernel_env(kernel):
         run_beam_case(cuda, *case)
 
 
-@pytest.mark.parametrize("kernel", ["resident2", "cluster8", "cluster4"])
+@pytest.mark.parametrize("kernel", ["resident2", "tmem", "cluster8", "cluster4"])
 def test_beam_ragged_blocks_one_launch(cuda, kernel):
     """four different block sizes in ONE launch: two get a per-launch exponent table, the others generate their
     candidate exponents in place; every block must equal the oracle on its own slice"""
@@ -156,8 +160,9 @@ def test_default_kernel_choice(cuda):
     assert lib.irec_beam_encode_path(9, 1000, 36, 20) == 108        # 100 + cluster size
     assert lib.irec_beam_encode_path(13, 1000, 20, 10) == 108
     assert lib.irec_beam_encode_path(24, 1000, 36, 20) == 104
-    assert lib.irec_beam_encode_path(302, 1000, 20, 10) == 2
-    assert lib.irec_beam_encode_path(1152, 1000, 36, 20) == 2
+    assert lib.irec_beam_encode_path(302, 1000, 20, 10) == 3        # tensor-memory kernel
+    assert lib.irec_beam_encode_path(1152, 1000, 36, 20) == 3
+    assert lib.irec_beam_encode_path(1152, 1000, 36, 32) == 2       # n_beams > 20: resident2
     assert lib.irec_beam_encode_path(1, 64, 36, 1) == 2
     assert lib.irec_beam_encode_path(1, 2500, 36, 4) == 0
 
