@@ -15,23 +15,30 @@
 // used -- and tcgen05.ld runs beside a saturated shared-memory pipe at no cost (measured: 1653 cycles per 480 conflicted
 // gathers with or without 14 tcgen05.ld.x4 per 40 gathers).
 //
-// Layout.  12 warps; warp w belongs to context c = (w >> 1) & 1, beam half h = w & 1, and is warp wi = w >> 2 of the three
-// warps of its TMEM lane quarter q = w & 3 = 2 c + h.  Quarter q, lane (row r, chunk l), holds
-//   columns [0, 32 HB)            the HB = BMAX / 2 beams of half h: beam lb, dim 32 l + i  at column 32 lb + i
-//   columns [32 HB, 32 HB + 128)  the coefficients of chunk l: sigma_aux, A, E, M, 32 columns each
-// so a context owns two quarters (one per beam half), the two contexts the whole 512-column allocation, and nothing is
-// replicated.  Shared memory keeps the quantile table (shared by both contexts), per context the scores / top-B scratch and
-// one 40 KB staging buffer through which re-materialised beams and new coefficients reach the quarters that hold them.
-// The contexts synchronise on named barriers (bar.sync 1 + c, 192 threads) and draw coder-blocks from the same queue; while
-// one runs its serial phases the other one scores.
+// Layout.  16 warps; warp w sits on scheduler / TMEM lane quarter q = w & 3 (hardware: a warp only reaches the TMEM lanes
+// 32 (w % 4) .. +31) and is warp wi = w >> 2 of its quarter; it belongs to context c = wi & 1, so EVERY scheduler hosts
+// two warps of each context and a context that scores can use all four issue ports while the other one is in a serial
+// phase (a first version bound contexts to quarters: each context then owned two schedulers and nothing overlapped).
+// The beams are split over the quarters in parts of HB = 5: with NQB = BMAX / 5 beam parts, quarter q holds part
+// bp = q % NQB of BOTH contexts and its warps score sample part sp = q / NQB (BMAX = 20: four beam parts, every warp scores
+// all samples against 5 beams; BMAX = 10: two beam parts x two sample halves, the parts replicated in quarters q and q + 2).
+// Quarter q, lane (row r, chunk l):
+//   columns [160 c, 160 c + 160)        the 5 beams of part bp of context c: beam lb, dim 32 l + i  at column 160 c + 32 lb + i
+//   columns [320 + 96 c, 320 + 96 c + 96) sigma_aux, A, E of chunk l for context c, 32 columns each
+// = all 512 columns; the fourth coefficient array (M) stays in shared memory (one LDS.128 per 60 gathers).  Shared memory
+// also keeps the quantile table (shared by both contexts), per context the scores / top-B scratch and one 40 KB staging
+// buffer through which re-materialised beams and new coefficients reach the quarters that hold them.  The contexts
+// synchronise on named barriers (bar.sync 1 + c, 256 threads) and draw coder-blocks from the same queue.
 #define IREC_R2_DEVICE_ONLY
 #include "irec_resident2.cuh"
 #include "irec_host.h"
+#include <stdio.h>
 
-#define TM_THREADS 384
-#define TM_CTX_THREADS 192
-#define TM_WARPS_PER_QUARTER 3
+#define TM_THREADS 512
+#define TM_CTX_THREADS 256
+#define TM_HB 5                    // beams per quarter and context
 #define TM_COLS 512
+#define TM_COEF_COL0 320           // first coefficient column (after 2 contexts x 5 beams x 32 dims)
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 wrappers (PTX ISA: tcgen05.alloc/dealloc/ld/st/wait/fence).  All .sync.aligned: every lane of the warp executes.
@@ -90,6 +97,7 @@ __device__ __forceinline__ void tm_tie16(float (&r)[16])
 //   (j_base[k] = s_k * D + first dim of the chunk) with the one-shot bank spreading of the general path.
 template <int HB, int NS, bool TAB>
 __device__ __forceinline__ void tm_score_chunk(const char* __restrict__ T2b, uint32_t tm_beams, uint32_t tm_coef,
+                                               const float4* __restrict__ M4, int lg,
                                                const uint32_t (&cb)[HB], int P, const uint2* __restrict__ tab_t,
                                                const uint32_t (&row)[NS], const uint16_t* __restrict__ dl4, const TfStream& st,
                                                const uint64_t (&j_base)[NS], float (&acc)[NS][HB])
@@ -119,16 +127,17 @@ __device__ __forceinline__ void tm_score_chunk(const char* __restrict__ T2b, uin
                 ad[k][2] = r2_spread_banks(r2_exp4(dl4, u.z)); ad[k][3] = r2_spread_banks(r2_exp4(dl4, u.w));
             }
         }
-        float sa[4], A[4], E[4], M[4];
+        float sa[4], A[4], E[4];
         tm_ld4(tm_coef + 4 * iq, sa);
         tm_ld4(tm_coef + 32 + 4 * iq, A);
         tm_ld4(tm_coef + 64 + 4 * iq, E);
-        tm_ld4(tm_coef + 96 + 4 * iq, M);
         float bm[HB][4];
 #pragma unroll
         for (int b = 0; b < HB; ++b) tm_ld4(tm_beams + 32 * b + 4 * iq, bm[b]);
+        const float4 Mq = M4[iq * P + lg];
+        const float M[4] = { Mq.x, Mq.y, Mq.z, Mq.w };
         tm_wait_ld();
-        tm_tie4(sa); tm_tie4(A); tm_tie4(E); tm_tie4(M);
+        tm_tie4(sa); tm_tie4(A); tm_tie4(E);
 #pragma unroll
         for (int b = 0; b < HB; ++b) tm_tie4(bm[b]);
 #pragma unroll
@@ -168,7 +177,7 @@ struct TmSrc {             // where the exponents of a partition come from
 };
 
 template <int HB, int NS, bool TAB>
-__device__ __forceinline__ void tm_score_round(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const uint32_t* s_cb,
+__device__ __forceinline__ void tm_score_round(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const float4* M4, const uint32_t* s_cb,
                                                const BeamGeom& g, int lane, const TmSrc& src, int sg_first,
                                                int sg_stride, int S, int Bcur, int boff, float* s_scores)
 {
@@ -190,7 +199,7 @@ __device__ __forceinline__ void tm_score_round(const char* T2b, uint32_t tm_beam
     for (int k = 0; k < NS; ++k)
 #pragma unroll
         for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
-    tm_score_chunk<HB, NS, TAB>(T2b, tm_beams, tm_coef, cb, g.P, src.tab_t, row, src.dl4, src.st, jb, acc);
+    tm_score_chunk<HB, NS, TAB>(T2b, tm_beams, tm_coef, M4, lg, cb, g.P, src.tab_t, row, src.dl4, src.st, jb, acc);
     float v[NS * HB];
 #pragma unroll
     for (int k = 0; k < NS; ++k)
@@ -200,28 +209,28 @@ __device__ __forceinline__ void tm_score_round(const char* T2b, uint32_t tm_beam
     r2_tree_store<NS * HB, NS * HB, HB, 0, R2LocalSink>(v, g.P, lane, (sg_first * g.SPW + lane / g.P), sg_stride * g.SPW, sink);
 }
 
-// all candidates of one partition that belong to this warp: the sample groups wi, wi + 3, ... against its beam half
+// all candidates of one partition that belong to this warp: sample groups u, u + NW, ... (u = this warp's index among the NW
+// warps of its context that score the same beam part) against the HB beams of its part
 template <int HB, bool TAB>
-__device__ __forceinline__ void tm_score_partition(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const uint32_t* s_cb,
-                                                   const BeamGeom& g, int lane, int wi, const TmSrc& src, int S,
-                                                   int Bcur, int boff, float* s_scores)
+__device__ __forceinline__ void tm_score_partition(const char* T2b, uint32_t tm_beams, uint32_t tm_coef, const float4* M4,
+                                                   const uint32_t* s_cb, const BeamGeom& g, int lane, int u, int NW, const TmSrc& src,
+                                                   int S, int Bcur, int boff, float* s_scores)
 {
-    constexpr int NW = TM_WARPS_PER_QUARTER;
     const int nsg = (S + g.SPW - 1) / g.SPW;
     int sg = 0;
-    // rounds of 3, then 2, then 1 sample groups per warp (all warps of the quarter take the same branch)
+    // rounds of 3, then 2, then 1 sample groups per warp (all warps take the same branch)
     while (nsg - sg > 2 * NW) {
-        if (sg + wi < nsg)   // groups beyond nsg are clamped inside (scores not stored)
-            tm_score_round<HB, 3, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        if (sg + u < nsg)   // groups beyond nsg are clamped inside (scores not stored)
+            tm_score_round<HB, 3, TAB>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, src, sg + u, NW, S, Bcur, boff, s_scores);
         sg += 3 * NW;
     }
     if (nsg - sg > NW) {
-        if (sg + wi < nsg)
-            tm_score_round<HB, 2, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        if (sg + u < nsg)
+            tm_score_round<HB, 2, TAB>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, src, sg + u, NW, S, Bcur, boff, s_scores);
         sg += 2 * NW;
     } else if (nsg - sg > 0) {
-        if (sg + wi < nsg)
-            tm_score_round<HB, 1, TAB>(T2b, tm_beams, tm_coef, s_cb, g, lane, src, sg + wi, NW, S, Bcur, boff, s_scores);
+        if (sg + u < nsg)
+            tm_score_round<HB, 1, TAB>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, src, sg + u, NW, S, Bcur, boff, s_scores);
         sg += NW;
     }
 }
@@ -241,17 +250,19 @@ struct TmemArgs {
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
     int tab_aux;
+    int score_lock;        // 1: the contexts take turns scoring (default); 0: free-running (IREC_TM_NO_LOCK=1, A/B runs)
+    long long* prof;       // nullptr, or [2 * gridDim.x][8] cycle counters per context (IREC_TM_PROFILE=1; diagnostics)
 };
 
 template <int BMAX>
 __host__ __device__ constexpr size_t tm_stage_floats(int DPmax)
 {
-    return (size_t)(BMAX * (DPmax / 2) > 4 * DPmax ? BMAX * (DPmax / 2) : 4 * DPmax);
+    return (size_t)(BMAX * (DPmax / 2) > 3 * DPmax ? BMAX * (DPmax / 2) : 3 * DPmax);
 }
 template <int BMAX>
 __host__ __device__ constexpr size_t tm_ctx_bytes(int DPmax, int NC)
 {
-    return 32 * sizeof(double) + sizeof(float) * ((size_t)NC + 256 + 32 + tm_stage_floats<BMAX>(DPmax)) +
+    return 32 * sizeof(double) + sizeof(float) * ((size_t)NC + 256 + 32 + (size_t)DPmax + tm_stage_floats<BMAX>(DPmax)) +
            sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32);
 }
 template <int BMAX>
@@ -263,15 +274,22 @@ __host__ __device__ constexpr size_t tm_smem_bytes(int DPmax, int NC)
 template <int BMAX>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemArgs a)
 {
-    static_assert(BMAX % 2 == 0 && BMAX * 16 + 128 <= TM_COLS, "beam half + coefficients must fit the 512 TMEM columns");
-    constexpr int HB = BMAX / 2;
-    constexpr uint32_t COEF0 = 32u * HB;
+    static_assert(BMAX == 5 || BMAX == 10 || BMAX == 20, "beam parts of 5 over 1, 2 or 4 TMEM lane quarters");
+    constexpr int HB = TM_HB;
+    constexpr int NQB = BMAX / HB;                 // beam parts (quarters that hold distinct beams)
+    constexpr int NSP = 4 / NQB;                   // sample parts (replicas of a beam part)
+    constexpr int NW = 2 * NSP;                    // warps of a context that score the same beam part
+    const bool USE_LOCK = a.score_lock != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_score_lock;                   // held by the context that is scoring (see "scoring turns" below)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = (warp >> 1) & 1, h = warp & 1, wi = warp >> 2;
+    const int q = warp & 3, wi = warp >> 2;        // scheduler / TMEM lane quarter, warp of the quarter
+    const int c = wi & 1, wj = wi >> 1;            // context, warp of (context, quarter)
+    const int bp = q % NQB, sp = q / NQB;          // beam part held by this quarter, sample part scored by it
+    const int u = sp * 2 + wj;                     // index among the NW warps that score beam part bp
     const int DPm = a.DPmax;
-    const WarpGroup grp{ (2 * wi + h) * 32 + lane, TM_CTX_THREADS, 1 + c };
+    const WarpGroup grp{ (wj * 4 + q) * 32 + lane, TM_CTX_THREADS, 1 + c };
     const int tid = grp.tid();
     constexpr int nt = TM_CTX_THREADS;
 
@@ -282,7 +300,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
     float* s_scores = reinterpret_cast<float*>(s_kl + 32);                               // [NC]
     float* s_gmax = s_scores + a.NC;                                                     // [256]
     float* s_wsc = s_gmax + 256;                                                         // [32] winners' scores
-    float* s_stage = s_wsc + 32;                                                         // staging: beams [BMAX][4][P] float4 / coefficients [4][DP]
+    float* s_M = s_wsc + 32;                                                             // [DPm] auxiliary-target means, CI layout
+    float* s_stage = s_M + DPm;                                                          // staging: beams [BMAX][4][P] float4 / coefficients [3][DP]
     int32_t* s_wid = reinterpret_cast<int32_t*>(s_stage + tm_stage_floats<BMAX>(DPm));   // [32] winners' flat ids
     int32_t* s_list = s_wid + 32;                                                        // [R2_TOPK_CAP]
     int32_t* s_ctl = s_list + R2_TOPK_CAP;                                               // [4]
@@ -290,6 +309,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
     int32_t* s_misc = s_hsum + 64;                                                       // [4]
     uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_misc + 4);                            // [32] 4 * dlog(h_b)
     float4* stage4 = reinterpret_cast<float4*>(s_stage);
+    const float4* M4 = reinterpret_cast<const float4*>(s_M);
 
     {
         const float4* src = reinterpret_cast<const float4*>(a.T2);
@@ -297,11 +317,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
         for (int i = threadIdx.x; i < IREC_T2_LEN / 4; i += blockDim.x) dst[i] = src[i];
     }
     if (warp == 0) tm_alloc(&s_tmem_base);
+    if (threadIdx.x == 0) s_score_lock = 0;
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
-    const uint32_t tm_q = s_tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);            // this warp's lane quarter
-    const uint32_t tm_coef = tm_q + COEF0;
+    const uint32_t tm_q = s_tmem_base + (((uint32_t)q * 32u) << 16);                     // this warp's lane quarter
+    const uint32_t tm_beams = tm_q + 160u * c;                                           // this context's beam part
+    const uint32_t tm_coef = tm_q + TM_COEF_COL0 + 96u * c;                              // sigma_aux, A, E
     const char* T2b = reinterpret_cast<const char*>(s_T2);
     const int slot = 2 * blockIdx.x + c;
     int2* hist = a.hist + (size_t)slot * a.max_aux * BMAX;
@@ -310,6 +332,17 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
     const int row_stride = DPm >> 2;
 
     auto ctx_sync = [&]() { tm_fence_before(); grp.sync(); tm_fence_after(); };
+    // phase clock of the context (thread 0 only; a.prof == nullptr in production): 0 setup, 1 score, 2 top-B + history,
+    // 3 re-materialisation, 4 next schedule, 5 waiting for the scoring turn, 6 variables, 7 blocks
+    long long pt = 0;
+    auto lap = [&](int phase) {
+        if (a.prof && tid == 0) {
+            const long long now = clock64();
+            a.prof[(size_t)slot * 8 + phase] += now - pt;
+            pt = now;
+        }
+    };
+    if (a.prof && tid == 0) pt = clock64();
 
     // Block queue: context 0 of every CTA starts with queue position blockIdx.x, everything else is drawn dynamically from
     // gridDim.x on -- no CTA holds two coder-blocks before every CTA holds one.
@@ -334,11 +367,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
 
         // ---- load + KL (coder.py:499-501) ----
         for (int i = tid; i < g.DP; i += nt) { g_cv[i] = 0.f; g_tv[i] = 0.f; g_dmu[i] = 0.f; g_cum[i] = 0.f; }
-        {   // the beams of this quarter start at zero (t = 0 scores the single empty beam; slots >= Bcur are never read back)
+        {   // the beams of this context start at zero (t = 0 scores the single empty beam; slots >= Bcur are never read back)
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int lb = wi; lb < HB; lb += TM_WARPS_PER_QUARTER) {
-                tm_st16(tm_q + 32 * lb, z, z, z, z);
-                tm_st16(tm_q + 32 * lb + 16, z, z, z, z);
+            for (int lb = wj; lb < HB; lb += 2) {
+                tm_st16(tm_beams + 32 * lb, z, z, z, z);
+                tm_st16(tm_beams + 32 * lb + 16, z, z, z, z);
             }
         }
         ctx_sync();
@@ -367,8 +400,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
         if (tid < 64) s_hsum[tid] = 0;
         int Bcur = 1, hb = 0;                      // hb: which half of s_hsum is current
 
-        // Coefficients of auxiliary variable t (beam_search_coder.py:64-77): every thread computes its dims into the staging
-        // buffer (CI layout, zeros in the padding), then each quarter copies all four arrays into its TMEM columns.
+        // Coefficients of an auxiliary variable (beam_search_coder.py:64-77): every thread computes its dims -- M straight into
+        // shared memory, sigma_aux / A / E into the staging buffer (CI layout, zeros in the padding) --, then the warps of every
+        // quarter copy the three arrays into the context's TMEM columns of their quarter.
         auto schedule_to_tmem = [&](float ratio, const int32_t* hs_new, int Knew) {
             for (int i = tid; i < g.DP; i += nt) {
                 SchedOut o;
@@ -378,11 +412,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                     o = beam_sched_dim(cv, g_tv[i], g_dmu[i], g_cum[i], ratio);
                     g_cum[i] = o.cum_next;
                 }
-                s_stage[i] = o.sa; s_stage[DPm + i] = o.A; s_stage[2 * DPm + i] = o.E; s_stage[3 * DPm + i] = o.M;
+                s_stage[i] = o.sa; s_stage[DPm + i] = o.A; s_stage[2 * DPm + i] = o.E; s_M[i] = o.M;
             }
             if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
             ctx_sync();
-            for (int pr = wi; pr < 32; pr += TM_WARPS_PER_QUARTER) {          // (array, quad) pairs of this quarter
+            for (int pr = wj; pr < 24; pr += 2) {                          // (array, quad) pairs of this quarter
                 const int arr = pr >> 3, iq = pr & 7;
                 tm_st4(tm_coef + 32 * arr + 4 * iq, stage4[arr * (DPm >> 2) + iq * g.P + lg]);
             }
@@ -390,6 +424,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
             ctx_sync();
         };
         schedule_to_tmem(a.ratio_tab[n_aux - 1], s_hsum, 1);      // empty index row: hash sum 0
+        lap(0);
 
         for (int t = 0; t < n_aux; ++t) {
             const int32_t* hs = s_hsum + 32 * hb;
@@ -397,21 +432,35 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
             src.tab_t = tab_blk ? tab_blk + (size_t)t * a.S * row_stride : nullptr;
             src.row_stride = row_stride; src.dl4 = a.dl4; src.st = tf_stream_seeded(a.seed + t, a.seed + t);
 
-            // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102): this warp's beam half ----
+            // Scoring turns.  Two contexts that share the shared-memory pipe fairly fall into lock-step (the one that lags gets
+            // the whole pipe while the other is in a serial phase and catches up), so their serial phases coincide and nothing
+            // overlaps (measured: 108 k cycles of joint scoring + 40 k of joint serial work per variable pair).  The scoring
+            // phase is therefore mutually exclusive: while one context scores with the whole pipe, the other runs top-B,
+            // re-materialisation and the next schedule, then waits for its turn.
+            if (USE_LOCK) {
+                if (tid == 0) {
+                    while (atomicCAS(&s_score_lock, 0, 1) != 0) __nanosleep(200);
+                }
+                grp.sync();
+            }
+            lap(5);
+            // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102): this warp's beam part, its share of the samples ----
             if (src.tab_t) {
                 if (Bcur == 1) {
-                    if (h == 0) tm_score_partition<1, true>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, 1, 0, s_scores);
-                } else if (h * HB < Bcur) {
-                    tm_score_partition<HB, true>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, Bcur, h * HB, s_scores);
+                    if (bp == 0) tm_score_partition<1, true>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, u, NW, src, a.S, 1, 0, s_scores);
+                } else if (bp * HB < Bcur) {
+                    tm_score_partition<HB, true>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, u, NW, src, a.S, Bcur, bp * HB, s_scores);
                 }
             } else {
                 if (Bcur == 1) {
-                    if (h == 0) tm_score_partition<1, false>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, 1, 0, s_scores);
-                } else if (h * HB < Bcur) {
-                    tm_score_partition<HB, false>(T2b, tm_q, tm_coef, s_cb, g, lane, wi, src, a.S, Bcur, h * HB, s_scores);
+                    if (bp == 0) tm_score_partition<1, false>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, u, NW, src, a.S, 1, 0, s_scores);
+                } else if (bp * HB < Bcur) {
+                    tm_score_partition<HB, false>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, u, NW, src, a.S, Bcur, bp * HB, s_scores);
                 }
             }
             ctx_sync();
+            if (USE_LOCK && tid == 0) atomicExch(&s_score_lock, 0);
+            lap(1);
 
             // ---- top-B (beam_search_coder.py:86-89,104-106) ----
             const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl, grp);
@@ -426,65 +475,69 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                 s_list[tid] = sj; s_list[32 + tid] = bj;
             }
             ctx_sync();
+            lap(2);
 
             // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93), 16 dims of every chunk per round.
-            //      A winner is computed by a warp of the quarter that holds its PARENT (lane = chunk), staged in shared memory,
-            //      and copied into the quarter that holds its new slot; all parents of a round are read before any slot is written.
+            //      A winner is computed by a warp of a quarter that holds its PARENT (lane = chunk), staged in shared memory,
+            //      and copied into the quarters that hold its new slot; all parents of a round are read before any slot is written.
             for (int rd = 0; rd < 2; ++rd) {
                 int mine = 0;
                 for (int j = 0; j < Kout; ++j) {
                     const int bj = s_list[32 + j];
-                    if (bj / HB != h) continue;                       // parent lives in the other half (warp-uniform)
-                    if ((mine++) % TM_WARPS_PER_QUARTER != wi) continue;
-                    const int sj = s_list[j], lb = bj - h * HB;
+                    if (bj / HB != bp) continue;                      // parent lives in another beam part (warp-uniform)
+                    if ((mine++) % NW != u) continue;
+                    const int sj = s_list[j], lb = bj - bp * HB;
                     uint2 ex[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int qq = 0; qq < 4; ++qq) {
                         if (src.tab_t) {
-                            ex[q] = __ldg(src.tab_t + (size_t)sj * row_stride + (4 * rd + q) * g.P + lg);
+                            ex[qq] = __ldg(src.tab_t + (size_t)sj * row_stride + (4 * rd + qq) * g.P + lg);
                         } else {                                      // 4 x uint16 word offsets, as the table stores them
-                            const int d0 = 32 * lg + 4 * (4 * rd + q);
-                            ex[q] = make_uint2(0u, 0u);
+                            const int d0 = 32 * lg + 4 * (4 * rd + qq);
+                            ex[qq] = make_uint2(0u, 0u);
                             if (d0 < D) {
-                                const uint4 u = tf_stream_quad_at(src.st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
-                                const uint32_t w0 = r2_exp4(a.dl4, u.x) >> 2, w1 = d0 + 1 < D ? r2_exp4(a.dl4, u.y) >> 2 : 0u;
-                                const uint32_t w2 = d0 + 2 < D ? r2_exp4(a.dl4, u.z) >> 2 : 0u, w3 = d0 + 3 < D ? r2_exp4(a.dl4, u.w) >> 2 : 0u;
-                                ex[q] = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+                                const uint4 uu = tf_stream_quad_at(src.st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                                const uint32_t w0 = r2_exp4(a.dl4, uu.x) >> 2, w1 = d0 + 1 < D ? r2_exp4(a.dl4, uu.y) >> 2 : 0u;
+                                const uint32_t w2 = d0 + 2 < D ? r2_exp4(a.dl4, uu.z) >> 2 : 0u, w3 = d0 + 3 < D ? r2_exp4(a.dl4, uu.w) >> 2 : 0u;
+                                ex[qq] = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
                             }
                         }
                     }
                     float par[16], sa[16];
-                    tm_ld16(tm_q + 32 * lb + 16 * rd, par);
+                    tm_ld16(tm_beams + 32 * lb + 16 * rd, par);
                     tm_ld16(tm_coef + 16 * rd, sa);
                     tm_wait_ld();
                     tm_tie16(par); tm_tie16(sa);
                     const uint32_t cb = s_cb[bj];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int qq = 0; qq < 4; ++qq) {
                         uint32_t e0, e1, e2, e3;
-                        r2_unpack(ex[q], e0, e1, e2, e3);
+                        r2_unpack(ex[qq], e0, e1, e2, e3);
                         float4 o;
-                        o.x = __fadd_rn(par[4 * q + 0], __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa[4 * q + 0]));
-                        o.y = __fadd_rn(par[4 * q + 1], __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa[4 * q + 1]));
-                        o.z = __fadd_rn(par[4 * q + 2], __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa[4 * q + 2]));
-                        o.w = __fadd_rn(par[4 * q + 3], __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa[4 * q + 3]));
+                        o.x = __fadd_rn(par[4 * qq + 0], __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa[4 * qq + 0]));
+                        o.y = __fadd_rn(par[4 * qq + 1], __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa[4 * qq + 1]));
+                        o.z = __fadd_rn(par[4 * qq + 2], __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa[4 * qq + 2]));
+                        o.w = __fadd_rn(par[4 * qq + 3], __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa[4 * qq + 3]));
                         // padding dims: sigma_aux = 0 and the parent is 0 there, so the padding stays zero
-                        if (lane < g.P) stage4[(j * 4 + q) * g.P + lg] = o;
+                        if (lane < g.P) stage4[(j * 4 + qq) * g.P + lg] = o;
                     }
                 }
                 ctx_sync();
-                for (int lb = wi; lb < HB; lb += TM_WARPS_PER_QUARTER) {
-                    const int j = h * HB + lb;
+                for (int lb = wj; lb < HB; lb += 2) {
+                    const int j = bp * HB + lb;
                     if (j < Kout)
-                        tm_st16(tm_q + 32 * lb + 16 * rd, stage4[(j * 4 + 0) * g.P + lg], stage4[(j * 4 + 1) * g.P + lg],
+                        tm_st16(tm_beams + 32 * lb + 16 * rd, stage4[(j * 4 + 0) * g.P + lg], stage4[(j * 4 + 1) * g.P + lg],
                                 stage4[(j * 4 + 2) * g.P + lg], stage4[(j * 4 + 3) * g.P + lg]);
                 }
                 tm_wait_st();
                 ctx_sync();
             }
 
+            lap(3);
             // ---- coefficients and table offsets c_b of the next auxiliary variable ----
             if (t + 1 < n_aux) schedule_to_tmem(a.ratio_tab[n_aux - 2 - t], hs_new, Kout);
+            lap(4);
+            if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 6] += 1;
             Bcur = Kout;
             hb ^= 1;
         }
@@ -499,10 +552,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                 j = e.y;
             }
         }
-        if (h == 0) {                              // beam 0 lives in the first quarter of the context
-            for (int iq = wi; iq < 8; iq += TM_WARPS_PER_QUARTER) {
+        if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 7] += 1;
+        if (q == 0) {                              // beam 0 lives in beam part 0 (quarter 0 holds a copy for every BMAX)
+            for (int iq = wj; iq < 8; iq += 2) {
                 float b0[4];
-                tm_ld4(tm_q + 4 * iq, b0);
+                tm_ld4(tm_beams + 4 * iq, b0);
                 tm_wait_ld();
                 tm_tie4(b0);
                 if (lane < g.P) {
@@ -529,7 +583,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
 // =============================================================================================
 static int tm_pick_bmax(int B)
 {
-    if (B > 1 && B <= 10) return 10;
+    if (B > 1 && B <= 5) return 5;
+    if (B > 5 && B <= 10) return 10;
     if (B > 10 && B <= 20) return 20;
     return -1;                                     // B = 1 and B > 20: the resident2 / resident kernels
 }
@@ -550,6 +605,7 @@ bool irec_tmem_plan(int nb, int max_D, int S, int B, TmemPlan* out)
     TmemPlan p{};
     bool ok = false;
     switch (tm_pick_bmax(B)) {
+        case 5: ok = tm_plan_t<5>(max_D, S, p); break;
         case 10: ok = tm_plan_t<10>(max_D, S, p); break;
         case 20: ok = tm_plan_t<20>(max_D, S, p); break;
         default: ok = false;
@@ -574,11 +630,37 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
     a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     a.hist = hist; a.work_counter = work_counter; a.DPmax = p.DPmax; a.NC = p.NC; a.sched = sched; a.order = order;
     a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux;
+    {
+        const char* le = getenv("IREC_TM_NO_LOCK");
+        a.score_lock = (le && le[0] == '1') ? 0 : 1;
+    }
+    a.prof = nullptr;
+    static long long* d_prof = nullptr;            // diagnostics only (IREC_TM_PROFILE=1): phase cycle counters, dumped to stderr
+    const char* pe = getenv("IREC_TM_PROFILE");
+    const bool prof_on = pe && pe[0] == '1';
+    if (prof_on) {
+        if (!d_prof) cudaMalloc(&d_prof, sizeof(long long) * 8 * 2 * 1024);
+        cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * 2 * 1024, s);
+        a.prof = d_prof;
+    }
     switch (p.bmax) {
+        case 5: k_beam_encode_tmem<5><<<p.grid, TM_THREADS, p.smem, s>>>(a); break;
         case 10: k_beam_encode_tmem<10><<<p.grid, TM_THREADS, p.smem, s>>>(a); break;
         case 20: k_beam_encode_tmem<20><<<p.grid, TM_THREADS, p.smem, s>>>(a); break;
         default: return irec_fail(IREC_E_INVALID, "irec_launch_tmem: unsupported beam capacity");
     }
     irec_count_launch();
+    if (prof_on) {
+        std::vector<long long> h(8 * 2 * p.grid);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double tot[8] = { 0 };
+        for (int i = 0; i < 2 * p.grid; ++i)
+            for (int k = 0; k < 8; ++k) tot[k] += (double)h[(size_t)i * 8 + k];
+        const double vars = tot[6] > 0 ? tot[6] : 1;
+        fprintf(stderr, "[tmem profile] contexts %d blocks %.0f variables %.0f | cycles per variable: wait-for-turn %.0f score %.0f topk %.0f remat %.0f sched %.0f | "
+                        "per block: setup %.0f\n", 2 * p.grid, tot[7], tot[6], tot[5] / vars, tot[1] / vars, tot[2] / vars,
+                tot[3] / vars, tot[4] / vars, tot[0] / (tot[7] > 0 ? tot[7] : 1));
+    }
     return irec_check_launch("k_beam_encode_tmem");
 }

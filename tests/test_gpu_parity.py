@@ -137,9 +137,12 @@ class kernel_env:
 def test_beam_resident_vs_oracle(cuda, case, kernel):
     """both generations of the persistent per-block kernel and the cluster-per-block kernel (with and without the
     per-launch exponent table) are bit-identical to the oracle"""
-    if kernel.startswith("tmem") and not 2 <= case[5] <= 20:
-        pytest.skip("k_beam_encode_tmem covers 2 <= n_beams <= 20 (others run resident2)")
     with kernel_env(kernel):
+        if kernel.startswith("tmem"):
+            from irec_b200 import native as N
+            S = int(np.exp(case[3] * case[4]))
+            if N.lib().irec_beam_encode_path(1, case[1], S, case[5]) != 3:
+                pytest.skip("sizes not covered by k_beam_encode_tmem (2 <= n_beams <= 20, S * 20 scores per context): resident2 runs them")
         run_beam_case(cuda, *case)
 
 
@@ -162,7 +165,8 @@ def test_default_kernel_choice(cuda):
     assert lib.irec_beam_encode_path(24, 1000, 36, 20) == 104
     assert lib.irec_beam_encode_path(302, 1000, 20, 10) == 3        # tensor-memory kernel
     assert lib.irec_beam_encode_path(1152, 1000, 36, 20) == 3
-    assert lib.irec_beam_encode_path(1152, 1000, 36, 32) == 2       # n_beams > 20: resident2
+    assert lib.irec_beam_encode_path(1152, 1000, 36, 32) == 1       # n_beams > 20: the first-generation kernel (a 32-beam matrix does not fit beside the 120 KB table)
+    assert lib.irec_beam_encode_path(1152, 256, 36, 32) == 2        # ... resident2 where it does
     assert lib.irec_beam_encode_path(1, 64, 36, 1) == 2
     assert lib.irec_beam_encode_path(1, 2500, 36, 4) == 0
 
