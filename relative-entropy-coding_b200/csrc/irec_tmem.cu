@@ -15,10 +15,17 @@
 // used -- and tcgen05.ld runs beside a saturated shared-memory pipe at no cost (measured: 1653 cycles per 480 conflicted
 // gathers with or without 14 tcgen05.ld.x4 per 40 gathers).
 //
-// Layout.  16 warps; warp w sits on scheduler / TMEM lane quarter q = w & 3 (hardware: a warp only reaches the TMEM lanes
-// 32 (w % 4) .. +31) and is warp wi = w >> 2 of its quarter; it belongs to context c = wi & 1, so EVERY scheduler hosts
-// two warps of each context and a context that scores can use all four issue ports while the other one is in a serial
-// phase (a first version bound contexts to quarters: each context then owned two schedulers and nothing overlapped).
+// Layout.  16 warps, two coder-block CONTEXTS per CTA, warp-specialised:
+//   * warp w sits on scheduler / TMEM lane quarter q = w & 3 (hardware: a warp only reaches TMEM lanes 32 (w % 4) .. +31);
+//   * warps 0..11 (three per quarter) are SCORING warps: they score the candidates of context 0, then of context 1, then of
+//     context 0 again, ... with the whole shared-memory pipe;
+//   * warps 12..15 (one per quarter) are SERIAL warps: while the scoring warps work on one context they run the other
+//     context's top-B, history, re-materialisation and next schedule (and, between coder-blocks, emit / queue / load / KL).
+//   Scores-ready and state-ready hand-offs are named barriers used as producer/consumer pairs (bar.arrive on one side,
+//   bar.sync on the other).  Two earlier versions let each context own its warps: bound to quarters, a context owned two
+//   schedulers and nothing overlapped; spread over all schedulers, the two contexts fell into lock-step (the one that lags
+//   gets the whole pipe while the other is in a serial phase and catches up), so their serial phases coincided -- 108 k
+//   cycles of joint scoring + 40 k of joint serial work per variable pair, no faster than one context.
 // The beams are split over the quarters in parts of HB = 5: with NQB = BMAX / 5 beam parts, quarter q holds part
 // bp = q % NQB of BOTH contexts and its warps score sample part sp = q / NQB (BMAX = 20: four beam parts, every warp scores
 // all samples against 5 beams; BMAX = 10: two beam parts x two sample halves, the parts replicated in quarters q and q + 2).
@@ -27,17 +34,23 @@
 //   columns [320 + 96 c, 320 + 96 c + 96) sigma_aux, A, E of chunk l for context c, 32 columns each
 // = all 512 columns; the fourth coefficient array (M) stays in shared memory (one LDS.128 per 60 gathers).  Shared memory
 // also keeps the quantile table (shared by both contexts), per context the scores / top-B scratch and one 40 KB staging
-// buffer through which re-materialised beams and new coefficients reach the quarters that hold them.  The contexts
-// synchronise on named barriers (bar.sync 1 + c, 256 threads) and draw coder-blocks from the same queue.
+// buffer through which re-materialised beams and new coefficients reach the quarters that hold them.
 #define IREC_R2_DEVICE_ONLY
 #include "irec_resident2.cuh"
 #include "irec_host.h"
 #include <stdio.h>
 
 #define TM_THREADS 512
-#define TM_CTX_THREADS 256
+#define TM_SCORE_WARPS 12          // warps 0..11: three per quarter
+#define TM_SERIAL_THREADS 128      // warps 12..15: one per quarter
+#define TM_BAR_SERIAL 1            // named barriers: serial warps among themselves
+#define TM_BAR_SCORES0 2           //   + c: scores of context c ready  (scoring warps arrive, serial warps wait)
+#define TM_BAR_STATE0 4            //   + c: state of context c ready   (serial warps arrive, scoring warps wait)
 #define TM_HB 5                    // beams per quarter and context
 #define TM_COLS 512
+#ifndef TM_NSBIG
+#define TM_NSBIG 4                 // sample groups per warp and round in the main scoring rounds
+#endif
 #define TM_COEF_COL0 320           // first coefficient column (after 2 contexts x 5 beams x 32 dims)
 
 // ---------------------------------------------------------------------------------------------
@@ -218,7 +231,14 @@ __device__ __forceinline__ void tm_score_partition(const char* T2b, uint32_t tm_
 {
     const int nsg = (S + g.SPW - 1) / g.SPW;
     int sg = 0;
-    // rounds of 3, then 2, then 1 sample groups per warp (all warps take the same branch)
+    // rounds of NSBIG sample groups per warp while that many are left (more accumulators per gathered operand: fewer TMEM /
+    // exponent loads per gather and fewer gathers in flight per warp), then rounds of 3, 2, 1 (all warps take the same branch)
+    if (HB > 1) {
+        while (nsg - sg >= TM_NSBIG * NW) {
+            tm_score_round<HB, TM_NSBIG, TAB>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, src, sg + u, NW, S, Bcur, boff, s_scores);
+            sg += TM_NSBIG * NW;
+        }
+    }
     while (nsg - sg > 2 * NW) {
         if (sg + u < nsg)   // groups beyond nsg are clamped inside (scores not stored)
             tm_score_round<HB, 3, TAB>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, src, sg + u, NW, S, Bcur, boff, s_scores);
@@ -250,25 +270,109 @@ struct TmemArgs {
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
     int tab_aux;
-    int score_lock;        // 1: the contexts take turns scoring (default); 0: free-running (IREC_TM_NO_LOCK=1, A/B runs)
+    int score_lock;        // unused (kept for A/B builds)
     long long* prof;       // nullptr, or [2 * gridDim.x][8] cycle counters per context (IREC_TM_PROFILE=1; diagnostics)
 };
 
+// shared memory: quantile table | scratch of the serial warps (one context at a time) | per context: scores, M, next coefficients
 template <int BMAX>
 __host__ __device__ constexpr size_t tm_stage_floats(int DPmax)
 {
-    return (size_t)(BMAX * (DPmax / 2) > 3 * DPmax ? BMAX * (DPmax / 2) : 3 * DPmax);
+    return (size_t)BMAX * (DPmax / 2);             // the parents' 16 dims per chunk of one re-materialisation round
 }
 template <int BMAX>
+__host__ __device__ constexpr size_t tm_serial_bytes(int DPmax)
+{
+    return 32 * sizeof(double) + sizeof(float) * (256 + 32 + tm_stage_floats<BMAX>(DPmax)) + sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 4);
+}
 __host__ __device__ constexpr size_t tm_ctx_bytes(int DPmax, int NC)
 {
-    return 32 * sizeof(double) + sizeof(float) * ((size_t)NC + 256 + 32 + (size_t)DPmax + tm_stage_floats<BMAX>(DPmax)) +
-           sizeof(int32_t) * (32 + R2_TOPK_CAP + 4 + 64 + 4 + 32);
+    return sizeof(float) * ((size_t)NC + (size_t)DPmax + 4 * (size_t)DPmax) + sizeof(int32_t) * (64 + 32);
 }
 template <int BMAX>
 __host__ __device__ constexpr size_t tm_smem_bytes(int DPmax, int NC)
 {
-    return sizeof(float) * (size_t)IREC_T2_LEN + 2 * tm_ctx_bytes<BMAX>(DPmax, NC) + 16;
+    return sizeof(float) * (size_t)IREC_T2_LEN + tm_serial_bytes<BMAX>(DPmax) + 2 * tm_ctx_bytes(DPmax, NC) + 16;
+}
+
+__device__ __forceinline__ void tm_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(TM_THREADS) : "memory"); }
+__device__ __forceinline__ void tm_bar_wait(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TM_THREADS) : "memory"); }
+
+// what the serial warps tell the scoring warps about a context (shared memory; valid after the state-ready barrier)
+struct TmCtl {
+    int finished;          // 1: no more coder-blocks for this context (the scoring warps stop visiting it)
+    int D;                 // dims of the current coder-block
+    int Bcur;              // beams alive
+    int t;                 // auxiliary variable to score
+    unsigned long long tab_blk;      // exponent table of this block size (const uint2*), 0 = in-place exponents
+};
+
+// KL, n_aux and status of every coder-block (coder.py:499-501), ahead of the persistent kernel: one CTA per block over the
+// whole GPU instead of 128 serial threads per SM evaluating float64 log / expm1 between coder-blocks
+__global__ void __launch_bounds__(256) k_tm_kl_status(const float* __restrict__ t_loc, const float* __restrict__ t_scale,
+                                                      const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                                                      const int64_t* __restrict__ gidx, const int64_t* __restrict__ offs, int nb,
+                                                      float omega, int max_aux, int ratio_len, int32_t* __restrict__ out_n_aux,
+                                                      int32_t* __restrict__ out_status)
+{
+    __shared__ double cs[32];
+    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+        const int64_t off = offs[blk];
+        const int D = (int)(offs[blk + 1] - off);
+        const int nch = (D + 31) >> 5;               // <= 32 (D <= 1024)
+        // canonical order: every 32-dim chunk is summed in ascending d by one thread, the chunk sums by the pairwise tree
+        for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
+            double acc = 0.0;
+            const int hi = min(D, 32 * ch + 32);
+            for (int d = 32 * ch; d < hi; ++d) {
+                const int64_t gi = gidx ? gidx[off + d] : off + d;
+                acc = __dadd_rn(acc, kl_dim(t_loc[gi], t_scale[gi], p_loc[gi], p_scale[gi]));
+            }
+            cs[ch] = acc;
+        }
+        const double kl = block_tree_sum_f64(cs, nch);
+        if (threadIdx.x == 0) {
+            const int n_aux = n_aux_from_kl((float)kl, omega);
+            int status = IREC_BLK_OK;
+            if (n_aux <= 0) status = IREC_BLK_BAD_KL;
+            else if (n_aux > max_aux || n_aux > ratio_len) status = IREC_BLK_TOO_LONG;
+            out_n_aux[blk] = n_aux;
+            out_status[blk] = status;
+        }
+        __syncthreads();
+    }
+}
+
+// Queue order: longest coder-blocks first (work ~ auxiliary variables x 32-dim chunks), so that the blocks handed out last --
+// the ones that decide when the launch ends -- are the short ones.  Counting sort into TM_ORDER_BUCKETS work classes (single CTA).
+#define TM_ORDER_BUCKETS 2048
+__global__ void __launch_bounds__(1024) k_tm_order(const int64_t* __restrict__ offs, const int32_t* __restrict__ n_aux,
+                                                   const int32_t* __restrict__ status, int nb, int32_t* __restrict__ order)
+{
+    __shared__ int s_cnt[TM_ORDER_BUCKETS];
+    __shared__ int s_max;
+    auto work = [&](int b) {
+        if (status[b] != IREC_BLK_OK) return 0;
+        const int64_t D = offs[b + 1] - offs[b];
+        return (int)min((int64_t)0x3fffff, (int64_t)n_aux[b] * ((D + 31) >> 5));
+    };
+    for (int i = threadIdx.x; i < TM_ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_max = 1;
+    __syncthreads();
+    int mx = 1;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) mx = max(mx, work(b));
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    const int wmax = s_max;
+    auto bucket = [&](int w) { return (TM_ORDER_BUCKETS - 1) - (int)(((int64_t)w * (TM_ORDER_BUCKETS - 1)) / wmax); };   // 0 = most work
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) atomicAdd(&s_cnt[bucket(work(b))], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < TM_ORDER_BUCKETS; ++i) { const int cnt = s_cnt[i]; s_cnt[i] = run; run += cnt; }   // exclusive prefix
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) order[atomicAdd(&s_cnt[bucket(work(b))], 1)] = b;
 }
 
 template <int BMAX>
@@ -278,38 +382,25 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
     constexpr int HB = TM_HB;
     constexpr int NQB = BMAX / HB;                 // beam parts (quarters that hold distinct beams)
     constexpr int NSP = 4 / NQB;                   // sample parts (replicas of a beam part)
-    constexpr int NW = 2 * NSP;                    // warps of a context that score the same beam part
-    const bool USE_LOCK = a.score_lock != 0;
+    constexpr int NW = 3 * NSP;                    // scoring warps that score the same beam part
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
-    __shared__ int s_score_lock;                   // held by the context that is scoring (see "scoring turns" below)
+    __shared__ TmCtl s_ctl2[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = warp & 3, wi = warp >> 2;        // scheduler / TMEM lane quarter, warp of the quarter
-    const int c = wi & 1, wj = wi >> 1;            // context, warp of (context, quarter)
+    const int q = warp & 3, wi = warp >> 2;        // scheduler / TMEM lane quarter, warp of the quarter (3 = the serial warp)
     const int bp = q % NQB, sp = q / NQB;          // beam part held by this quarter, sample part scored by it
-    const int u = sp * 2 + wj;                     // index among the NW warps that score beam part bp
     const int DPm = a.DPmax;
-    const WarpGroup grp{ (wj * 4 + q) * 32 + lane, TM_CTX_THREADS, 1 + c };
-    const int tid = grp.tid();
-    constexpr int nt = TM_CTX_THREADS;
+    const int row_stride = DPm >> 2;
 
     // ---- shared memory carve-up ----
     float* s_T2 = reinterpret_cast<float*>(smem_raw);                                    // [IREC_T2_LEN], both contexts
-    unsigned char* cbase = smem_raw + sizeof(float) * (size_t)IREC_T2_LEN + (size_t)c * tm_ctx_bytes<BMAX>(DPm, a.NC);
-    double* s_kl = reinterpret_cast<double*>(cbase);                                     // [32]
-    float* s_scores = reinterpret_cast<float*>(s_kl + 32);                               // [NC]
-    float* s_gmax = s_scores + a.NC;                                                     // [256]
-    float* s_wsc = s_gmax + 256;                                                         // [32] winners' scores
-    float* s_M = s_wsc + 32;                                                             // [DPm] auxiliary-target means, CI layout
-    float* s_stage = s_M + DPm;                                                          // staging: beams [BMAX][4][P] float4 / coefficients [3][DP]
-    int32_t* s_wid = reinterpret_cast<int32_t*>(s_stage + tm_stage_floats<BMAX>(DPm));   // [32] winners' flat ids
-    int32_t* s_list = s_wid + 32;                                                        // [R2_TOPK_CAP]
-    int32_t* s_ctl = s_list + R2_TOPK_CAP;                                               // [4]
-    int32_t* s_hsum = s_ctl + 4;                                                         // [2][32]
-    int32_t* s_misc = s_hsum + 64;                                                       // [4]
-    uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_misc + 4);                            // [32] 4 * dlog(h_b)
-    float4* stage4 = reinterpret_cast<float4*>(s_stage);
-    const float4* M4 = reinterpret_cast<const float4*>(s_M);
+    unsigned char* ser_base = smem_raw + sizeof(float) * (size_t)IREC_T2_LEN;            // scratch of the serial warps
+    auto ctx_base = [&](int c) { return ser_base + tm_serial_bytes<BMAX>(DPm) + (size_t)c * tm_ctx_bytes(DPm, a.NC); };
+    auto ctx_scores = [&](int c) { return reinterpret_cast<float*>(ctx_base(c)); };      // [NC]
+    auto ctx_M = [&](int c) { return ctx_scores(c) + a.NC; };                            // [DPm] auxiliary-target means, CI layout
+    auto ctx_next = [&](int c) { return ctx_M(c) + DPm; };                               // [4][DPm] coefficients of the NEXT variable
+    auto ctx_hsum = [&](int c) { return reinterpret_cast<int32_t*>(ctx_next(c) + 4 * DPm); };   // [2][32]
+    auto ctx_cb = [&](int c) { return reinterpret_cast<uint32_t*>(ctx_hsum(c) + 64); };  // [32] 4 * dlog(h_b)
 
     {
         const float4* src = reinterpret_cast<const float4*>(a.T2);
@@ -317,133 +408,35 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
         for (int i = threadIdx.x; i < IREC_T2_LEN / 4; i += blockDim.x) dst[i] = src[i];
     }
     if (warp == 0) tm_alloc(&s_tmem_base);
-    if (threadIdx.x == 0) s_score_lock = 0;
+    if (threadIdx.x < 2) { s_ctl2[threadIdx.x].finished = 0; }
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
     const uint32_t tm_q = s_tmem_base + (((uint32_t)q * 32u) << 16);                     // this warp's lane quarter
-    const uint32_t tm_beams = tm_q + 160u * c;                                           // this context's beam part
-    const uint32_t tm_coef = tm_q + TM_COEF_COL0 + 96u * c;                              // sigma_aux, A, E
     const char* T2b = reinterpret_cast<const char*>(s_T2);
-    const int slot = 2 * blockIdx.x + c;
-    int2* hist = a.hist + (size_t)slot * a.max_aux * BMAX;
-    float* g_cv = a.sched + (size_t)slot * 4 * DPm;                                      // global scratch (this context only), CI layout
-    float* g_tv = g_cv + DPm; float* g_dmu = g_tv + DPm; float* g_cum = g_dmu + DPm;
-    const int row_stride = DPm >> 2;
 
-    auto ctx_sync = [&]() { tm_fence_before(); grp.sync(); tm_fence_after(); };
-    // phase clock of the context (thread 0 only; a.prof == nullptr in production): 0 setup, 1 score, 2 top-B + history,
-    // 3 re-materialisation, 4 next schedule, 5 waiting for the scoring turn, 6 variables, 7 blocks
-    long long pt = 0;
-    auto lap = [&](int phase) {
-        if (a.prof && tid == 0) {
-            const long long now = clock64();
-            a.prof[(size_t)slot * 8 + phase] += now - pt;
-            pt = now;
-        }
-    };
-    if (a.prof && tid == 0) pt = clock64();
-
-    // Block queue: context 0 of every CTA starts with queue position blockIdx.x, everything else is drawn dynamically from
-    // gridDim.x on -- no CTA holds two coder-blocks before every CTA holds one.
-    bool first = (c == 0);
-    for (;;) {
-        ctx_sync();
-        if (tid == 0) s_misc[0] = first ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.work_counter, 1);
-        first = false;
-        ctx_sync();
-        if (s_misc[0] >= a.nb) break;
-        const int blk = a.order ? a.order[s_misc[0]] : s_misc[0];
-        const int64_t off = a.offs[blk];
-        const int D = (int)(a.offs[blk + 1] - off);
-        const BeamGeom g = make_geom(D);
-        const int lg = lane & (g.P - 1);
-        const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
-        if (a.tab) {
-#pragma unroll
-            for (int k = 0; k < R2_MAX_SIZES; ++k)
-                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
-        }
-
-        // ---- load + KL (coder.py:499-501) ----
-        for (int i = tid; i < g.DP; i += nt) { g_cv[i] = 0.f; g_tv[i] = 0.f; g_dmu[i] = 0.f; g_cum[i] = 0.f; }
-        {   // the beams of this context start at zero (t = 0 scores the single empty beam; slots >= Bcur are never read back)
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int lb = wj; lb < HB; lb += 2) {
-                tm_st16(tm_beams + 32 * lb, z, z, z, z);
-                tm_st16(tm_beams + 32 * lb + 16, z, z, z, z);
-            }
-        }
-        ctx_sync();
-        for (int ch = tid; ch < g.nch; ch += nt) {
-            double acc = 0.0;
-            const int hi = min(D, 32 * ch + 32);
-            for (int d = 32 * ch; d < hi; ++d) {
-                const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
-                const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
-                acc = __dadd_rn(acc, kl_dim(tl, ts, pl, ps));
-                const int ci = ci_index(d, g.P);
-                g_cv[ci] = __fmul_rn(ps, ps);
-                g_tv[ci] = __fmul_rn(ts, ts);
-                g_dmu[ci] = __fadd_rn(tl, -pl);
-            }
-            s_kl[ch] = acc;
-        }
-        const double kld = block_tree_sum_f64(s_kl, g.nch, grp);
-        const int n_aux = n_aux_from_kl((float)kld, a.omega);
-        int status = IREC_BLK_OK;
-        if (n_aux <= 0) status = IREC_BLK_BAD_KL;
-        else if (n_aux > a.max_aux || n_aux > a.ratio_len) status = IREC_BLK_TOO_LONG;
-        if (tid == 0) { a.out_n_aux[blk] = n_aux; a.out_status[blk] = status; }
-        if (status != IREC_BLK_OK) continue;
-
-        if (tid < 64) s_hsum[tid] = 0;
-        int Bcur = 1, hb = 0;                      // hb: which half of s_hsum is current
-
-        // Coefficients of an auxiliary variable (beam_search_coder.py:64-77): every thread computes its dims -- M straight into
-        // shared memory, sigma_aux / A / E into the staging buffer (CI layout, zeros in the padding) --, then the warps of every
-        // quarter copy the three arrays into the context's TMEM columns of their quarter.
-        auto schedule_to_tmem = [&](float ratio, const int32_t* hs_new, int Knew) {
-            for (int i = tid; i < g.DP; i += nt) {
-                SchedOut o;
-                o.sa = 0.f; o.A = 0.f; o.E = 0.f; o.M = 0.f; o.cum_next = 0.f;
-                const float cv = g_cv[i];
-                if (cv != 0.f) {
-                    o = beam_sched_dim(cv, g_tv[i], g_dmu[i], g_cum[i], ratio);
-                    g_cum[i] = o.cum_next;
-                }
-                s_stage[i] = o.sa; s_stage[DPm + i] = o.A; s_stage[2 * DPm + i] = o.E; s_M[i] = o.M;
-            }
-            if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
-            ctx_sync();
-            for (int pr = wj; pr < 24; pr += 2) {                          // (array, quad) pairs of this quarter
-                const int arr = pr >> 3, iq = pr & 7;
-                tm_st4(tm_coef + 32 * arr + 4 * iq, stage4[arr * (DPm >> 2) + iq * g.P + lg]);
-            }
-            tm_wait_st();
-            ctx_sync();
-        };
-        schedule_to_tmem(a.ratio_tab[n_aux - 1], s_hsum, 1);      // empty index row: hash sum 0
-        lap(0);
-
-        for (int t = 0; t < n_aux; ++t) {
-            const int32_t* hs = s_hsum + 32 * hb;
+    if (warp < TM_SCORE_WARPS) {
+        // ======================================= scoring warps =======================================
+        const int u = sp * 3 + wi;                 // index among the NW warps that score beam part bp
+        bool done[2] = { false, false };
+        for (int turn = 0; !(done[0] && done[1]); ++turn) {
+            const int c = turn & 1;
+            if (done[c]) continue;
+            tm_bar_wait(TM_BAR_STATE0 + c);        // the serial warps have prepared (or retired) context c
+            tm_fence_after();
+            const TmCtl ctl = s_ctl2[c];
+            if (ctl.finished) { done[c] = true; continue; }
+            const BeamGeom g = make_geom(ctl.D);
+            const uint32_t tm_beams = tm_q + 160u * c;
+            const uint32_t tm_coef = tm_q + TM_COEF_COL0 + 96u * c;
+            const float4* M4 = reinterpret_cast<const float4*>(ctx_M(c));
+            const uint32_t* s_cb = ctx_cb(c);
+            float* s_scores = ctx_scores(c);
+            const uint2* tab_blk = reinterpret_cast<const uint2*>(ctl.tab_blk);
             TmSrc src;
-            src.tab_t = tab_blk ? tab_blk + (size_t)t * a.S * row_stride : nullptr;
-            src.row_stride = row_stride; src.dl4 = a.dl4; src.st = tf_stream_seeded(a.seed + t, a.seed + t);
-
-            // Scoring turns.  Two contexts that share the shared-memory pipe fairly fall into lock-step (the one that lags gets
-            // the whole pipe while the other is in a serial phase and catches up), so their serial phases coincide and nothing
-            // overlaps (measured: 108 k cycles of joint scoring + 40 k of joint serial work per variable pair).  The scoring
-            // phase is therefore mutually exclusive: while one context scores with the whole pipe, the other runs top-B,
-            // re-materialisation and the next schedule, then waits for its turn.
-            if (USE_LOCK) {
-                if (tid == 0) {
-                    while (atomicCAS(&s_score_lock, 0, 1) != 0) __nanosleep(200);
-                }
-                grp.sync();
-            }
-            lap(5);
+            src.tab_t = tab_blk ? tab_blk + (size_t)ctl.t * a.S * row_stride : nullptr;
+            src.row_stride = row_stride; src.dl4 = a.dl4; src.st = tf_stream_seeded(a.seed + ctl.t, a.seed + ctl.t);
+            const int Bcur = ctl.Bcur;
             // ---- score all S * Bcur candidates (beam_search_coder.py:79-84,97-102): this warp's beam part, its share of the samples ----
             if (src.tab_t) {
                 if (Bcur == 1) {
@@ -458,117 +451,309 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                     tm_score_partition<HB, false>(T2b, tm_beams, tm_coef, M4, s_cb, g, lane, u, NW, src, a.S, Bcur, bp * HB, s_scores);
                 }
             }
-            ctx_sync();
-            if (USE_LOCK && tid == 0) atomicExch(&s_score_lock, 0);
-            lap(1);
+            tm_fence_before();
+            tm_bar_arrive(TM_BAR_SCORES0 + c);
+        }
+    } else {
+        // ======================================= serial warps =======================================
+        const WarpGroup grp{ q * 32 + lane, TM_SERIAL_THREADS, TM_BAR_SERIAL };
+        const int tid = grp.tid();
+        constexpr int nt = TM_SERIAL_THREADS;
+        auto ser_sync = [&]() { tm_fence_before(); grp.sync(); tm_fence_after(); };
+        // scratch shared by both contexts (the serial warps work on one context at a time)
+        double* s_kl = reinterpret_cast<double*>(ser_base);                                  // [32] (unused since k_tm_kl_status; keeps the layout aligned)
+        float* s_gmax = reinterpret_cast<float*>(s_kl + 32);                                 // [256]
+        float* s_wsc = s_gmax + 256;                                                         // [32] winners' scores
+        float* s_stage = s_wsc + 32;                                                         // parents of a round: [BMAX][4][P] float4
+        int32_t* s_wid = reinterpret_cast<int32_t*>(s_stage + tm_stage_floats<BMAX>(DPm));   // [32] winners' flat ids
+        int32_t* s_list = s_wid + 32;                                                        // [R2_TOPK_CAP]
+        int32_t* s_ctl = s_list + R2_TOPK_CAP;                                               // [4]
+        int32_t* s_misc = s_ctl + 4;                                                         // [4]
+        float4* stage4 = reinterpret_cast<float4*>(s_stage);
 
-            // ---- top-B (beam_search_coder.py:86-89,104-106) ----
-            const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl, grp);
+        // per-context state that lives in this thread's registers across the turns
+        struct Blk { int active, blk, D, n_aux, t, Bcur, hb; int64_t off; const uint2* tab_blk; };
+        Blk st[2];
+        st[0].active = 0; st[1].active = 0;
+        bool retired[2] = { false, false };
+        bool first = true;                         // context 0 starts with queue position blockIdx.x (see below)
+        long long pt = 0;
+        if (a.prof && tid == 0) pt = clock64();
 
-            // ---- history + hash sums of the new beams (:92-95); (s_j, b_j) for the re-materialisation ----
-            int32_t* hs_new = s_hsum + 32 * (hb ^ 1);
-            if (tid < Kout) {
-                const int f = s_wid[tid];
-                const int sj = f / Bcur, bj = f - sj * Bcur;
-                hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
-                hs_new[tid] = hsum_extend(hs[bj], sj, t);
-                s_list[tid] = sj; s_list[32 + tid] = bj;
-            }
-            ctx_sync();
-            lap(2);
-
-            // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93), 16 dims of every chunk per round.
-            //      A winner is computed by a warp of a quarter that holds its PARENT (lane = chunk), staged in shared memory,
-            //      and copied into the quarters that hold its new slot; all parents of a round are read before any slot is written.
-            for (int rd = 0; rd < 2; ++rd) {
-                int mine = 0;
-                for (int j = 0; j < Kout; ++j) {
-                    const int bj = s_list[32 + j];
-                    if (bj / HB != bp) continue;                      // parent lives in another beam part (warp-uniform)
-                    if ((mine++) % NW != u) continue;
-                    const int sj = s_list[j], lb = bj - bp * HB;
-                    uint2 ex[4];
+        for (int turn = 0; !(retired[0] && retired[1]); ++turn) {
+            const int c = turn & 1;
+            if (retired[c]) continue;
+            Blk& B_ = st[c];
+            // ---- this context's shared memory, global scratch and TMEM columns ----
+            float* s_scores = ctx_scores(c);
+            float* s_M = ctx_M(c);
+            float* s_next = ctx_next(c);
+            int32_t* s_hsum = ctx_hsum(c);
+            uint32_t* s_cb = ctx_cb(c);
+            const uint32_t tm_beams = tm_q + 160u * c;
+            const uint32_t tm_coef = tm_q + TM_COEF_COL0 + 96u * c;
+            const int slot = 2 * blockIdx.x + c;
+            int2* hist = a.hist + (size_t)slot * a.max_aux * BMAX;
+            float* g_cv = a.sched + (size_t)slot * 4 * DPm;                                  // global scratch (this context only), CI layout
+            float* g_tv = g_cv + DPm; float* g_dmu = g_tv + DPm; float* g_cum = g_dmu + DPm;
+            auto lap = [&](int phase) {
+                if (a.prof && tid == 0) {
+                    const long long now = clock64();
+                    a.prof[(size_t)slot * 8 + phase] += now - pt;
+                    pt = now;
+                }
+            };
+            // Coefficients of an auxiliary variable (beam_search_coder.py:64-77) into the context's NEXT buffer (CI layout, zeros
+            // in the padding).  They do not depend on the winners, so they are computed while the scoring warps still score the
+            // context's current variable.
+            auto compute_next = [&](const BeamGeom& g, float ratio) {
+                // all global loads of the thread's (at most 8) dims first: the L2 round trips overlap instead of adding up
+                float in[8][4];
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        if (src.tab_t) {
-                            ex[qq] = __ldg(src.tab_t + (size_t)sj * row_stride + (4 * rd + qq) * g.P + lg);
-                        } else {                                      // 4 x uint16 word offsets, as the table stores them
-                            const int d0 = 32 * lg + 4 * (4 * rd + qq);
-                            ex[qq] = make_uint2(0u, 0u);
-                            if (d0 < D) {
-                                const uint4 uu = tf_stream_quad_at(src.st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
-                                const uint32_t w0 = r2_exp4(a.dl4, uu.x) >> 2, w1 = d0 + 1 < D ? r2_exp4(a.dl4, uu.y) >> 2 : 0u;
-                                const uint32_t w2 = d0 + 2 < D ? r2_exp4(a.dl4, uu.z) >> 2 : 0u, w3 = d0 + 3 < D ? r2_exp4(a.dl4, uu.w) >> 2 : 0u;
-                                ex[qq] = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+                for (int r = 0; r < 8; ++r) {
+                    const int i = tid + r * nt;
+                    const bool on = i < g.DP;
+                    in[r][0] = on ? g_cv[i] : 0.f; in[r][1] = on ? g_tv[i] : 0.f;
+                    in[r][2] = on ? g_dmu[i] : 0.f; in[r][3] = on ? g_cum[i] : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = tid + r * nt;
+                    if (i < g.DP) {
+                        SchedOut o;
+                        o.sa = 0.f; o.A = 0.f; o.E = 0.f; o.M = 0.f; o.cum_next = 0.f;
+                        if (in[r][0] != 0.f) {
+                            o = beam_sched_dim(in[r][0], in[r][1], in[r][2], in[r][3], ratio);
+                            g_cum[i] = o.cum_next;
+                        }
+                        s_next[i] = o.sa; s_next[DPm + i] = o.A; s_next[2 * DPm + i] = o.E; s_next[3 * DPm + i] = o.M;
+                    }
+                }
+            };
+            // NEXT buffer -> the scoring warps' operands: sigma_aux / A / E into the context's TMEM columns of every quarter, M into
+            // shared memory, table offsets c_b of the new beams.  Callers synchronise before (NEXT complete) and hand over after.
+            auto install_next = [&](const BeamGeom& g, const int32_t* hs_new, int Knew) {
+                const int lg = lane & (g.P - 1);
+                const float4* next4 = reinterpret_cast<const float4*>(s_next);
+                for (int pr = 0; pr < 24; ++pr) {                              // (array, quad) pairs
+                    const int arr = pr >> 3, iq = pr & 7;
+                    tm_st4(tm_coef + 32 * arr + 4 * iq, next4[arr * (DPm >> 2) + iq * g.P + lg]);
+                }
+                for (int i = tid; i < g.DP; i += nt) s_M[i] = s_next[3 * DPm + i];
+                if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
+                tm_wait_st();
+            };
+
+            if (B_.active) {
+                const BeamGeom g = make_geom(B_.D);
+                const int lg = lane & (g.P - 1);
+                const int D = B_.D, t = B_.t, Bcur = B_.Bcur;
+                // =========== while the scoring warps score variable t of this context: coefficients of variable t + 1 ===========
+                if (t + 1 < B_.n_aux) compute_next(g, a.ratio_tab[B_.n_aux - 2 - t]);
+                lap(4);
+                // =========== scores of variable t ready: select, re-materialise, install t + 1 ===========
+                tm_bar_wait(TM_BAR_SCORES0 + c);
+                tm_fence_after();
+                lap(5);
+                const int32_t* hs = s_hsum + 32 * B_.hb;
+                TmSrc src;
+                src.tab_t = B_.tab_blk ? B_.tab_blk + (size_t)t * a.S * row_stride : nullptr;
+                src.row_stride = row_stride; src.dl4 = a.dl4; src.st = tf_stream_seeded(a.seed + t, a.seed + t);
+
+                // ---- top-B (beam_search_coder.py:86-89,104-106) ----
+                const int Kout = block_topk(s_scores, nullptr, a.S * Bcur, a.B, s_wsc, s_wid, s_gmax, s_list, R2_TOPK_CAP, s_ctl, grp);
+
+                // ---- history + hash sums of the new beams (:92-95); (s_j, b_j) for the re-materialisation ----
+                int32_t* hs_new = s_hsum + 32 * (B_.hb ^ 1);
+                if (tid < Kout) {
+                    const int f = s_wid[tid];
+                    const int sj = f / Bcur, bj = f - sj * Bcur;
+                    hist[(size_t)t * BMAX + tid] = make_int2(sj, bj);
+                    hs_new[tid] = hsum_extend(hs[bj], sj, t);
+                    s_list[tid] = sj; s_list[32 + tid] = bj;
+                }
+                ser_sync();
+                lap(2);
+
+                // ---- re-materialise the winners: beam_j <- beam_{b_j} + a(s_j, b_j)  (:92-93), 16 dims of every chunk per round:
+                //      (1) every quarter copies the 16 dims of its (old) beams into the staging buffer -- parents readable by all;
+                //      (2) every quarter computes ITS OWN five slots from the staged parents (lane = chunk) and stores them straight
+                //          into its TMEM columns: five winners per serial warp whatever the parents are, no write before all reads.
+                for (int rd = 0; rd < 2; ++rd) {
+                    uint2 ex[HB][4];                           // exponent rows of this quarter's winners, requested first (L2 latency)
+#pragma unroll
+                    for (int lb = 0; lb < HB; ++lb) {
+                        const int j = bp * HB + lb;
+                        const int sj = j < Kout ? s_list[j] : 0;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            ex[lb][qq] = make_uint2(0u, 0u);
+                            if (j >= Kout) continue;
+                            if (src.tab_t) {
+                                ex[lb][qq] = __ldg(src.tab_t + (size_t)sj * row_stride + (4 * rd + qq) * g.P + lg);
+                            } else {                                      // 4 x uint16 word offsets, as the table stores them
+                                const int d0 = 32 * lg + 4 * (4 * rd + qq);
+                                if (d0 < D) {
+                                    const uint4 uu = tf_stream_quad_at(src.st, (uint64_t)sj * (uint64_t)D + (uint64_t)d0);
+                                    const uint32_t w0 = r2_exp4(a.dl4, uu.x) >> 2, w1 = d0 + 1 < D ? r2_exp4(a.dl4, uu.y) >> 2 : 0u;
+                                    const uint32_t w2 = d0 + 2 < D ? r2_exp4(a.dl4, uu.z) >> 2 : 0u, w3 = d0 + 3 < D ? r2_exp4(a.dl4, uu.w) >> 2 : 0u;
+                                    ex[lb][qq] = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+                                }
                             }
                         }
                     }
-                    float par[16], sa[16];
-                    tm_ld16(tm_beams + 32 * lb + 16 * rd, par);
+                    if (sp == 0) {                             // one replica of every beam part stages its beams
+#pragma unroll
+                        for (int lb = 0; lb < HB; ++lb) {
+                            const int b = bp * HB + lb;
+                            if (b < Bcur) {
+                                float par[16];
+                                tm_ld16(tm_beams + 32 * lb + 16 * rd, par);
+                                tm_wait_ld();
+                                tm_tie16(par);
+                                if (lane < g.P) {
+#pragma unroll
+                                    for (int qq = 0; qq < 4; ++qq)
+                                        stage4[(b * 4 + qq) * g.P + lg] = make_float4(par[4 * qq], par[4 * qq + 1], par[4 * qq + 2], par[4 * qq + 3]);
+                                }
+                            }
+                        }
+                    }
+                    float sa[16];
                     tm_ld16(tm_coef + 16 * rd, sa);
                     tm_wait_ld();
-                    tm_tie16(par); tm_tie16(sa);
-                    const uint32_t cb = s_cb[bj];
+                    tm_tie16(sa);
+                    ser_sync();
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        uint32_t e0, e1, e2, e3;
-                        r2_unpack(ex[qq], e0, e1, e2, e3);
-                        float4 o;
-                        o.x = __fadd_rn(par[4 * qq + 0], __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa[4 * qq + 0]));
-                        o.y = __fadd_rn(par[4 * qq + 1], __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa[4 * qq + 1]));
-                        o.z = __fadd_rn(par[4 * qq + 2], __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa[4 * qq + 2]));
-                        o.w = __fadd_rn(par[4 * qq + 3], __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa[4 * qq + 3]));
-                        // padding dims: sigma_aux = 0 and the parent is 0 there, so the padding stays zero
-                        if (lane < g.P) stage4[(j * 4 + qq) * g.P + lg] = o;
+                    for (int lb = 0; lb < HB; ++lb) {
+                        const int j = bp * HB + lb;
+                        if (j < Kout) {
+                            const int bj = s_list[32 + j];
+                            const uint32_t cb = s_cb[bj];
+                            float4 o[4];
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                uint32_t e0, e1, e2, e3;
+                                r2_unpack(ex[lb][qq], e0, e1, e2, e3);
+                                const float4 par = stage4[(bj * 4 + qq) * g.P + lg];
+                                o[qq].x = __fadd_rn(par.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + e0 + cb), sa[4 * qq + 0]));
+                                o[qq].y = __fadd_rn(par.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + e1 + cb), sa[4 * qq + 1]));
+                                o[qq].z = __fadd_rn(par.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + e2 + cb), sa[4 * qq + 2]));
+                                o[qq].w = __fadd_rn(par.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + e3 + cb), sa[4 * qq + 3]));
+                                // padding dims: sigma_aux = 0 and the parent is 0 there, so the padding stays zero
+                            }
+                            tm_st16(tm_beams + 32 * lb + 16 * rd, o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    tm_wait_st();
+                    ser_sync();                                // staging is reused by the next round / the next turn
+                }
+                lap(3);
+                B_.Bcur = Kout;
+                B_.hb ^= 1;
+                B_.t = t + 1;
+                if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 6] += 1;
+                if (B_.t < B_.n_aux) {
+                    // ---- hand the context back with the coefficients and table offsets c_b of the next auxiliary variable ----
+                    install_next(g, hs_new, Kout);
+                    if (tid == 0) { s_ctl2[c].Bcur = Kout; s_ctl2[c].t = B_.t; }
+                    lap(1);
+                    tm_fence_before();
+                    tm_bar_arrive(TM_BAR_STATE0 + c);
+                    continue;
+                }
+                // ---- coder-block finished: indices of the best beam (trace the back-pointers) and its sample (:118-122) ----
+                if (tid == 0) {
+                    int j = 0;
+                    int32_t* oi = a.out_indices + (size_t)B_.blk * a.max_aux;
+                    for (int tt = B_.n_aux - 1; tt >= 0; --tt) {
+                        const int2 e = hist[(size_t)tt * BMAX + j];
+                        oi[tt] = e.x;
+                        j = e.y;
                     }
                 }
-                ctx_sync();
-                for (int lb = wj; lb < HB; lb += 2) {
-                    const int j = bp * HB + lb;
-                    if (j < Kout)
-                        tm_st16(tm_beams + 32 * lb + 16 * rd, stage4[(j * 4 + 0) * g.P + lg], stage4[(j * 4 + 1) * g.P + lg],
-                                stage4[(j * 4 + 2) * g.P + lg], stage4[(j * 4 + 3) * g.P + lg]);
-                }
-                tm_wait_st();
-                ctx_sync();
-            }
-
-            lap(3);
-            // ---- coefficients and table offsets c_b of the next auxiliary variable ----
-            if (t + 1 < n_aux) schedule_to_tmem(a.ratio_tab[n_aux - 2 - t], hs_new, Kout);
-            lap(4);
-            if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 6] += 1;
-            Bcur = Kout;
-            hb ^= 1;
-        }
-
-        // ---- emit: indices of the best beam (trace the back-pointers) and its sample (:118-122) ----
-        if (tid == 0) {
-            int j = 0;
-            int32_t* oi = a.out_indices + (size_t)blk * a.max_aux;
-            for (int t = n_aux - 1; t >= 0; --t) {
-                const int2 e = hist[(size_t)t * BMAX + j];
-                oi[t] = e.x;
-                j = e.y;
-            }
-        }
-        if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 7] += 1;
-        if (q == 0) {                              // beam 0 lives in beam part 0 (quarter 0 holds a copy for every BMAX)
-            for (int iq = wj; iq < 8; iq += 2) {
-                float b0[4];
-                tm_ld4(tm_beams + 4 * iq, b0);
-                tm_wait_ld();
-                tm_tie4(b0);
-                if (lane < g.P) {
+                if (q == 0) {                          // beam 0 lives in beam part 0 (quarter 0 holds a copy for every BMAX)
+                    for (int iq = 0; iq < 8; ++iq) {
+                        float b0[4];
+                        tm_ld4(tm_beams + 4 * iq, b0);
+                        tm_wait_ld();
+                        tm_tie4(b0);
+                        if (lane < g.P) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int d = 32 * lg + 4 * iq + e;
-                        if (d < D) {
-                            const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
-                            a.out_sample[gi] = __fadd_rn(b0[e], a.p_loc[gi]);
+                            for (int e = 0; e < 4; ++e) {
+                                const int d = 32 * lg + 4 * iq + e;
+                                if (d < D) {
+                                    const int64_t gi = a.gidx ? a.gidx[B_.off + d] : B_.off + d;
+                                    a.out_sample[gi] = __fadd_rn(b0[e], a.p_loc[gi]);
+                                }
+                            }
                         }
                     }
                 }
+                if (a.prof && tid == 0) a.prof[(size_t)slot * 8 + 7] += 1;
+                B_.active = 0;
+            }
+
+            // =========== next coder-block of this context (queue, load, first schedule) ===========
+            // Block queue: context 0 of every CTA starts with queue position blockIdx.x, everything else is drawn dynamically
+            // from gridDim.x on -- no CTA holds two coder-blocks before every CTA holds one.
+            for (;;) {
+                ser_sync();
+                if (tid == 0) s_misc[0] = (first && c == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.work_counter, 1);
+                ser_sync();
+                if (c == 0) first = false;
+                const int pos = s_misc[0];
+                if (pos >= a.nb) {
+                    retired[c] = true;
+                    if (tid == 0) s_ctl2[c].finished = 1;
+                    tm_fence_before();
+                    tm_bar_arrive(TM_BAR_STATE0 + c);     // the scoring warps learn that this context is finished
+                    break;
+                }
+                const int blk = a.order ? a.order[pos] : pos;
+                if (a.out_status[blk] != IREC_BLK_OK) continue;       // KL not finite / too many auxiliary variables (k_tm_kl_status)
+                const int n_aux = a.out_n_aux[blk];
+                const int64_t off = a.offs[blk];
+                const int D = (int)(a.offs[blk + 1] - off);
+                const BeamGeom g = make_geom(D);
+                const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
+                if (a.tab) {
+#pragma unroll
+                    for (int k = 0; k < R2_MAX_SIZES; ++k)
+                        if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
+                }
+                // ---- load (CI layout, zero padding) ----
+                for (int i = tid; i < g.DP; i += nt) {
+                    const int l = (i >> 2) & (g.P - 1), iq = i / (4 * g.P), e = i & 3;       // CI(P): i = (iq * P + l) * 4 + e
+                    const int d = 32 * l + 4 * iq + e;
+                    float cv = 0.f, tv = 0.f, dmu = 0.f;
+                    if (d < D) {
+                        const int64_t gi = a.gidx ? a.gidx[off + d] : off + d;
+                        const float tl = a.t_loc[gi], ts = a.t_scale[gi], pl = a.p_loc[gi], ps = a.p_scale[gi];
+                        cv = __fmul_rn(ps, ps); tv = __fmul_rn(ts, ts); dmu = __fadd_rn(tl, -pl);
+                    }
+                    g_cv[i] = cv; g_tv[i] = tv; g_dmu[i] = dmu; g_cum[i] = 0.f;
+                }
+                {   // the beams of this context start at zero (t = 0 scores the single empty beam; slots >= Bcur are never read back)
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int lb = 0; lb < HB; ++lb) {
+                        tm_st16(tm_beams + 32 * lb, z, z, z, z);
+                        tm_st16(tm_beams + 32 * lb + 16, z, z, z, z);
+                    }
+                }
+                if (tid < 64) s_hsum[tid] = 0;
+                compute_next(g, a.ratio_tab[n_aux - 1]);    // same thread, same dims as the load above: no barrier needed in between
+                ser_sync();
+                install_next(g, s_hsum, 1);                 // empty index row: hash sum 0
+                B_.active = 1; B_.blk = blk; B_.D = D; B_.n_aux = n_aux; B_.t = 0; B_.Bcur = 1; B_.hb = 0; B_.off = off; B_.tab_blk = tab_blk;
+                if (tid == 0) {
+                    s_ctl2[c].D = D; s_ctl2[c].Bcur = 1; s_ctl2[c].t = 0;
+                    s_ctl2[c].tab_blk = reinterpret_cast<unsigned long long>(tab_blk);
+                }
+                lap(0);
+                tm_fence_before();
+                tm_bar_arrive(TM_BAR_STATE0 + c);
+                break;
             }
         }
     }
@@ -630,9 +815,13 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
     a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     a.hist = hist; a.work_counter = work_counter; a.DPmax = p.DPmax; a.NC = p.NC; a.sched = sched; a.order = order;
     a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux;
-    {
-        const char* le = getenv("IREC_TM_NO_LOCK");
-        a.score_lock = (le && le[0] == '1') ? 0 : 1;
+    a.score_lock = 0;
+    k_tm_kl_status<<<std::min(nb, 8 * irec_device().sm_count), 256, 0, s>>>(t_loc, t_scale, p_loc, p_scale, gidx, offs, nb, omega, max_aux,
+                                                                           a.ratio_len, out_n_aux, out_status);
+    irec_count_launch();
+    if (order) {
+        k_tm_order<<<1, 1024, 0, s>>>(offs, out_n_aux, out_status, nb, const_cast<int32_t*>(order));
+        irec_count_launch();
     }
     a.prof = nullptr;
     static long long* d_prof = nullptr;            // diagnostics only (IREC_TM_PROFILE=1): phase cycle counters, dumped to stderr
@@ -658,9 +847,9 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
         for (int i = 0; i < 2 * p.grid; ++i)
             for (int k = 0; k < 8; ++k) tot[k] += (double)h[(size_t)i * 8 + k];
         const double vars = tot[6] > 0 ? tot[6] : 1;
-        fprintf(stderr, "[tmem profile] contexts %d blocks %.0f variables %.0f | cycles per variable: wait-for-turn %.0f score %.0f topk %.0f remat %.0f sched %.0f | "
-                        "per block: setup %.0f\n", 2 * p.grid, tot[7], tot[6], tot[5] / vars, tot[1] / vars, tot[2] / vars,
-                tot[3] / vars, tot[4] / vars, tot[0] / (tot[7] > 0 ? tot[7] : 1));
+        fprintf(stderr, "[tmem profile] contexts %d blocks %.0f variables %.0f | serial warps, cycles per variable: next coefficients %.0f waiting for scores %.0f topk %.0f remat %.0f install %.0f | "
+                        "per block: emit + queue + load + first schedule %.0f\n", 2 * p.grid, tot[7], tot[6], tot[4] / vars, tot[5] / vars, tot[2] / vars,
+                tot[3] / vars, tot[1] / vars, tot[0] / (tot[7] > 0 ? tot[7] : 1));
     }
     return irec_check_launch("k_beam_encode_tmem");
 }
