@@ -249,16 +249,23 @@ def bench_c5(ctx, args):
         S5 = int(np.exp(float(omega) * EXTRA))
         d = [torch.as_tensor(a, device=dev).contiguous() for a in (mu, sig, pl, ps)]
         blk = engine.ShardedBeamBlock(C5_DIMS, S5, NBEAMS, omega, max_aux=256, device=dev)
-        idx, sample = blk.encode(*d, seed=SEED)                   # eager: warm-up + result
-        idx_g, sample_g = blk.encode_graphed(*d, seed=SEED)       # captures the loop; must reproduce the eager result
+        idx, sample = blk.encode(*d, seed=SEED)                   # multi-launch state machine, eager: warm-up + result
+        fused = blk.fused_available()
+        if fused:
+            idx_g, sample_g = blk.encode_fused(*d, seed=SEED)     # one cooperative launch for all variables
+        else:
+            idx_g, sample_g = blk.encode_graphed(*d, seed=SEED)   # captures the loop; must reproduce the eager result
         graph_ok = bool(idx_g == idx and torch.equal(sample_g, sample))
         times = []
         for _ in range(args.c5_reps):
             ctx["barrier"]()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            n_aux = blk.init(*d, seed=SEED)
-            blk._graphs[n_aux].replay()
+            if fused:
+                blk.encode_fused(*d, seed=SEED)
+            else:
+                n_aux = blk.init(*d, seed=SEED)
+                blk._graphs[n_aux].replay()
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -272,7 +279,8 @@ def bench_c5(ctx, args):
                "candidates_per_sec": cand / (ms * 1e-3), "candidate_dims_per_sec": cand * C5_DIMS / (ms * 1e-3),
                "exchange": ("peer-memory stores (irec_p2p_exchange)" if blk.p2p is not None else
                             ("nccl all_gather" if world > 1 else "none")),
-               "cuda_graph": True, "graph_equals_eager": graph_ok}
+               "launch": ("one cooperative launch for all variables (k_gp_fused)" if fused else "7 launches per variable, CUDA graph"),
+               "equals_multi_launch_path": graph_ok}
         if rank == 0:
             if S5 <= 1.2e5:
                 from oracle import oracle as O

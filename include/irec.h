@@ -179,6 +179,18 @@ size_t irec_p2p_exchange_bytes(int B, int world);
 int irec_p2p_exchange(void* const* peer_bufs, int rank, int world, int B, const irec_record_t* local_records_and_count,
                       irec_record_t* out_records, int32_t* out_counts, void* stream);
 
+/* The same loop as ONE cooperative launch per coder-block (all auxiliary variables; beam_search_coder.py:66-109): every
+ * CTA keeps a replica of the block state in shared memory, scores its share of this rank's candidates [s_begin, s_end),
+ * and per auxiliary variable the last CTA to arrive merges the grid's top-B lists, exchanges the rank list with the peers
+ * through peer_bufs (layout and protocol of irec_p2p_exchange; NULL with world = 1) and publishes the winners.  Replaces
+ * the seven launches per variable of step_score / p2p_exchange / step_commit where the block state fits shared memory
+ * (D <= 256 at 20 beams; IREC_E_CAPACITY otherwise).  Call between irec_beam_state_init and irec_beam_state_finish;
+ * every rank must call it for the same block. */
+int irec_beam_fused_fits(int D, int B);          /* 1: the fused launch covers these sizes on the current device */
+size_t irec_beam_fused_workspace_bytes(int B, int world);
+int irec_beam_encode_fused(void* state, int D, int B, int64_t s_begin, int64_t s_end, void* const* peer_bufs, int rank,
+                           int world, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- importance sampler (rec/coding/importance_sampling.py, samplers.py:61-101) -------------- */
 
 /* encode_gaussian_importance_sample with alpha = inf (importance_sampling.py:9-79): one partition,

@@ -789,6 +789,302 @@ __global__ void k_gp_finish(void* state, const int64_t* __restrict__ gidx, int64
     }
 }
 
+// =============================================================================================
+// K5 fused: ALL auxiliary variables of one coder-block in ONE persistent launch, candidates spread over the grid and,
+// across GPUs, over the ranks (beam_search_coder.py:66-109 with the argsort at :86 split at every level).
+// The multi-launch path above spends ~65 us per auxiliary variable in seven dependent small launches (params, score,
+// merge, exchange, merge, commit, flip) -- more than a GPU's share of the scoring below S ~ 10^6.  Here every CTA keeps
+// its OWN replica of the block state in shared memory (schedule inputs, coefficients, both beam buffers, hash sums; the
+// per-variable schedule and the winners' re-materialisation are computed redundantly by every CTA: a few thousand
+// flops), so one variable needs a single all-to-all point:
+//   score own sample groups -> CTA top-B -> publish records -> arrive
+//   the LAST CTA to arrive merges the grid's lists (rank top-B), exchanges it with the peer ranks (stores into their
+//   exchange buffers over NVLink + sequence flags, as k_p2p_exchange), merges the world's lists, publishes the winners
+//   every CTA waits for the winners (acquire spin on a sequence word), commits them into its replica, goes on.
+// Cooperative launch (all CTAs co-resident: the spin waits cannot deadlock).  Limits: the replica must fit beside the
+// 120 KB quantile table -- D <= 256 at 20 beams; larger blocks take the multi-launch path.
+// =============================================================================================
+#define P2P_FLAG_OFF 64            // layout of a rank's exchange buffer: see k_p2p_exchange below
+#define P2P_SLOT_OFF 128
+struct FusedArgs {
+    void* state;                     // BeamState (k_gp_init has filled it); receives the final beams / history / header
+    const float* T2; const uint16_t* dl4; const float* ratio_tab;
+    int64_t s_begin, s_end;          // this rank's candidate range
+    irec_record_t* lists; int32_t* list_cnt;      // [grid][B], [grid]
+    float* g_sc; int32_t* g_id;      // merge scratch [(grid + world) * B]
+    irec_record_t* win; int32_t* nwin;            // [2][32], [2]   (parity = t & 1)
+    int32_t* sync;                   // [0] arrivals, [1] published sequence (both zeroed before the launch)
+    int32_t* const* peer_bufs; int rank, world;   // nullptr / 0 / 1 on a single GPU
+    int cand_cap;
+};
+
+template <int BMAX>
+__global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BeamStateHdr* hdr = reinterpret_cast<BeamStateHdr*>(a.state);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (hdr->status != IREC_BLK_OK) return;
+    BeamGeom g;
+    g.D = hdr->D; g.P = hdr->P; g.nslots = hdr->nslots; g.DP = hdr->DP; g.nch = (g.D + 31) >> 5; g.SPW = 32 / g.P;
+    const int B = hdr->B, n_aux = hdr->n_aux, DP = g.DP;
+    const int64_t seed = hdr->seed;
+    const int cap = a.cand_cap;
+    constexpr int HB = R2Pass<BMAX>::HB;
+
+    float* s_T2 = reinterpret_cast<float*>(smem_raw);                // [IREC_T2_LEN]
+    float* s_cv = s_T2 + IREC_T2_LEN;                                // replica: cv, tv, dmu, cum, sa, A, E, M  [8][DP]
+    float* s_tv = s_cv + DP; float* s_dmu = s_tv + DP; float* s_cum = s_dmu + DP;
+    float* s_sa = s_cum + DP; float* s_A = s_sa + DP; float* s_E = s_A + DP; float* s_M = s_E + DP;
+    float* s_beams = s_M + DP;                                       // [2][BMAX][DP]
+    float* s_csc = s_beams + 2 * BMAX * DP;                          // [cap]
+    int32_t* s_cid = reinterpret_cast<int32_t*>(s_csc + cap);        // [cap]
+    float* s_gmax = reinterpret_cast<float*>(s_cid + cap);           // [GP2_THREADS]
+    float* s_wsc = s_gmax + GP2_THREADS;                             // [32]
+    int32_t* s_wid = reinterpret_cast<int32_t*>(s_wsc + 32);         // [32]
+    int32_t* s_list = s_wid + 32;                                    // [TOPK_CAP]
+    int32_t* s_ctl = s_list + TOPK_CAP;                              // [4]
+    int32_t* s_cnt = s_ctl + 4;                                      // [1] candidate count
+    float* s_tau = reinterpret_cast<float*>(s_cnt + 1);              // [1]
+    int32_t* s_flag = reinterpret_cast<int32_t*>(s_tau + 1);         // [2] last-arriver flag, exchange sequence
+    uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_flag + 2);        // [32] 4 * dlog(h_b)
+    int32_t* s_hsum = reinterpret_cast<int32_t*>(s_cb + 32);         // [2][32]
+    irec_record_t* s_win = reinterpret_cast<irec_record_t*>(s_hsum + 64);   // [32]
+
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.T2);
+        float4* dst = reinterpret_cast<float4*>(s_T2);
+        for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
+    }
+    for (int i = tid; i < DP; i += nt) {
+        s_cv[i] = st_arr(a.state, 0, DP)[i]; s_tv[i] = st_arr(a.state, 1, DP)[i]; s_dmu[i] = st_arr(a.state, 2, DP)[i];
+        s_cum[i] = 0.f; s_sa[i] = 0.f; s_A[i] = 0.f; s_E[i] = 0.f; s_M[i] = 0.f;
+    }
+    for (int i = tid; i < 2 * BMAX * DP; i += nt) s_beams[i] = 0.f;
+    if (tid < 64) s_hsum[tid] = 0;
+    __syncthreads();
+
+    const int lg = lane & (g.P - 1);
+    const char* T2b = reinterpret_cast<const char*>(s_T2);
+    const int nq = DP >> 2;
+    // contiguous range of sample groups per CTA
+    const int64_t nsg = (a.s_end - a.s_begin + g.SPW - 1) / g.SPW;
+    const int64_t per = (nsg + gridDim.x - 1) / gridDim.x;
+    const int64_t sg0 = (int64_t)blockIdx.x * per, sg1 = min(nsg, sg0 + per);
+    const int64_t s_hi64 = min(a.s_end, a.s_begin + sg1 * g.SPW);
+    const int s_hi = (int)s_hi64;
+    int Bcur = 1, cur = 0;
+
+    for (int t = 0; t < n_aux; ++t) {
+        // ---- schedule of this auxiliary variable (every CTA for itself) ----
+        const float ratio = a.ratio_tab[n_aux - 1 - t];
+        for (int i = tid; i < DP; i += nt) {
+            const float c = s_cv[i];
+            if (c != 0.f) {
+                const SchedOut o = beam_sched_dim(c, s_tv[i], s_dmu[i], s_cum[i], ratio);
+                s_sa[i] = o.sa; s_A[i] = o.A; s_E[i] = o.E; s_M[i] = o.M; s_cum[i] = o.cum_next;
+            }
+        }
+        const int32_t* hs = s_hsum + 32 * cur;
+        if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs[tid]) - 1)) : 0u;
+        if (tid == 0) { *s_cnt = 0; *s_tau = __int_as_float(0xff800000); }
+        __syncthreads();
+        const float4* sa4 = reinterpret_cast<const float4*>(s_sa);
+        const float4* A4 = reinterpret_cast<const float4*>(s_A);
+        const float4* E4 = reinterpret_cast<const float4*>(s_E);
+        const float4* M4 = reinterpret_cast<const float4*>(s_M);
+        const float4* beams4 = reinterpret_cast<const float4*>(s_beams + (size_t)cur * BMAX * DP);
+        const TfStream st = tf_stream_seeded(seed + t, seed + t);
+
+        // ---- score this CTA's sample groups, keep its best B (as k_gp_score_topb2) ----
+        for (int64_t base = sg0; base < sg1; base += (int64_t)nwarps * GP2_NS) {
+            uint64_t jb[GP2_NS];
+            uint32_t row[GP2_NS];
+#pragma unroll
+            for (int k = 0; k < GP2_NS; ++k) {
+                const int64_t s = a.s_begin + (base + warp + (int64_t)k * nwarps) * g.SPW + lane / g.P;
+                const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // groups beyond the range: clamped, not stored
+                jb[k] = s_eff * (uint64_t)g.D + (uint64_t)(32 * lg);
+                row[k] = 0u;
+            }
+            const int s_first = (int)(a.s_begin + (base + warp) * g.SPW + lane / g.P);
+            const float tau = *s_tau;
+#pragma unroll 1
+            for (int boff = 0; boff < BMAX; boff += HB) {
+                if (boff >= Bcur) break;
+                float acc[GP2_NS][HB];
+#pragma unroll
+                for (int k = 0; k < GP2_NS; ++k)
+#pragma unroll
+                    for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
+                r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
+                                                        g.P, lg, st, jb, nullptr, row, acc);
+                float v[GP2_NS * HB];
+#pragma unroll
+                for (int k = 0; k < GP2_NS; ++k)
+#pragma unroll
+                    for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
+                const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, s_hi };
+                r2_tree_store<GP2_NS * HB, GP2_NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
+            }
+            __syncthreads();
+            const int cnt = *s_cnt;
+            if (cnt > B) {
+                const int Kc = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+                if (tid < Kc) { s_csc[tid] = s_wsc[tid]; s_cid[tid] = s_wid[tid]; }
+                if (tid == 0) { *s_cnt = Kc; if (Kc == B) *s_tau = s_wsc[Kc - 1]; }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        const int Kcta = block_topk(s_csc, s_cid, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+
+        // ---- publish, arrive; the last CTA merges, exchanges, publishes the winners ----
+        if (tid < Kcta) {
+            irec_record_t r;
+            const int f = s_wid[tid];
+            r.score = s_wsc[tid]; r.s = f / Bcur; r.b = f - r.s * Bcur; r.pad = 0;
+            a.lists[(size_t)blockIdx.x * B + tid] = r;
+        }
+        if (tid == 0) a.list_cnt[blockIdx.x] = Kcta;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int ticket = atomicAdd(&a.sync[0], 1);
+            s_flag[0] = (ticket == (t + 1) * (int)gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        const int parity = t & 1;
+        if (s_flag[0]) {
+            __threadfence();
+            // rank top-B over the grid's lists
+            if (tid == 0) *s_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < (int)gridDim.x * B; i += nt) {
+                const int li = i / B, e = i - li * B;
+                if (e < __ldcg(a.list_cnt + li)) {
+                    const int pos = atomicAdd(s_cnt, 1);
+                    const int4 v = __ldcg(reinterpret_cast<const int4*>(a.lists) + i);      // (score bits, s, b, pad) straight from L2
+                    a.g_sc[pos] = __int_as_float(v.x);
+                    a.g_id[pos] = v.y * Bcur + v.z;
+                }
+            }
+            __syncthreads();
+            int K = block_topk(a.g_sc, a.g_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+            if (a.world > 1) {
+                // exchange the rank lists over peer memory (protocol of k_p2p_exchange), then merge the world's lists
+                int32_t* mine = a.peer_bufs[a.rank];
+                if (tid == 0) s_flag[1] = mine[0] + 1;
+                __syncthreads();
+                const int seq = s_flag[1], W = (B + 1) * 4, par = seq & 1;
+                for (int i = tid; i < a.world * W; i += nt) {
+                    const int r = i / W, w = i - r * W;
+                    int32_t val;
+                    if (w < B * 4) {
+                        const int e = w >> 2, c = w & 3;
+                        const int f = e < K ? s_wid[e] : 0;
+                        const int sj = f / Bcur;
+                        val = e < K ? (c == 0 ? __float_as_int(s_wsc[e]) : (c == 1 ? sj : (c == 2 ? f - sj * Bcur : 0))) : 0;
+                    } else {
+                        val = (w == B * 4) ? K : 0;
+                    }
+                    a.peer_bufs[r][P2P_SLOT_OFF + (par * a.world + a.rank) * W + w] = val;
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid < a.world) {
+                    int32_t* flag = a.peer_bufs[tid] + P2P_FLAG_OFF + a.rank;
+                    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+                    const int32_t* want = mine + P2P_FLAG_OFF + tid;
+                    int got;
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(got) : "l"(want) : "memory");
+                    } while (got - seq < 0);
+                }
+                __syncthreads();
+                const volatile int32_t* slots = mine + P2P_SLOT_OFF + par * a.world * W;
+                if (tid == 0) *s_cnt = 0;
+                __syncthreads();
+                for (int i = tid; i < a.world * B; i += nt) {
+                    const int r = i / B, e = i - r * B;
+                    if (e < slots[r * W + B * 4]) {
+                        const int pos = atomicAdd(s_cnt, 1);
+                        a.g_sc[pos] = __int_as_float(slots[r * W + e * 4]);
+                        a.g_id[pos] = slots[r * W + e * 4 + 1] * Bcur + slots[r * W + e * 4 + 2];
+                    }
+                }
+                __syncthreads();
+                K = block_topk(a.g_sc, a.g_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+                if (tid == 0) mine[0] = seq;
+            }
+            if (tid < K) {
+                irec_record_t r;
+                const int f = s_wid[tid];
+                r.score = s_wsc[tid]; r.s = f / Bcur; r.b = f - r.s * Bcur; r.pad = 0;
+                a.win[parity * 32 + tid] = r;
+            }
+            if (tid == 0) a.nwin[parity] = K;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sync + 1), "r"(t + 1) : "memory");
+        }
+        if (tid == 0) {
+            int got;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(a.sync + 1) : "memory");
+            } while (got < t + 1);
+        }
+        __syncthreads();
+        const int K = __ldcg(a.nwin + parity);
+        if (tid < K) {
+            const int4 v = __ldcg(reinterpret_cast<const int4*>(a.win + parity * 32) + tid);
+            irec_record_t r;
+            r.score = __int_as_float(v.x); r.s = v.y; r.b = v.z; r.pad = 0;
+            s_win[tid] = r;
+        }
+        __syncthreads();
+
+        // ---- commit into this CTA's replica: new beams (other buffer), hash sums; CTA 0 keeps the history ----
+        {
+            const float4* old4 = reinterpret_cast<const float4*>(s_beams + (size_t)cur * BMAX * DP);
+            float4* new4 = reinterpret_cast<float4*>(s_beams + (size_t)(cur ^ 1) * BMAX * DP);
+            for (int task = tid; task < nq * K; task += nt) {
+                const int j = task / nq, qq = task - j * nq;
+                const int iq = qq / g.P, l = qq - iq * g.P;
+                const int d0 = 32 * l + 4 * iq;
+                const int sj = s_win[j].s, bj = s_win[j].b;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d0 < g.D) {
+                    const uint32_t cb = s_cb[bj];
+                    const uint4 u = tf_stream_quad_at(st, (uint64_t)sj * (uint64_t)g.D + (uint64_t)d0);
+                    const float4 sa = sa4[qq];
+                    const float4 ob = old4[bj * nq + qq];
+                    o.x = __fadd_rn(ob.x, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(a.dl4, u.x) + cb), sa.x));
+                    o.y = __fadd_rn(ob.y, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(a.dl4, u.y) + cb), sa.y));
+                    o.z = __fadd_rn(ob.z, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(a.dl4, u.z) + cb), sa.z));
+                    o.w = __fadd_rn(ob.w, __fmul_rn(*reinterpret_cast<const float*>(T2b + r2_exp4(a.dl4, u.w) + cb), sa.w));
+                    // dims beyond D inside the last quad: sigma_aux = 0 and the parent is 0 there, so the padding stays zero
+                }
+                new4[j * nq + qq] = o;
+            }
+            int32_t* hs_new = s_hsum + 32 * (cur ^ 1);
+            if (tid < K) {
+                hs_new[tid] = hsum_extend(hs[s_win[tid].b], s_win[tid].s, t);
+                if (blockIdx.x == 0) st_hist(a.state, B, DP)[(size_t)t * 32 + tid] = make_int2(s_win[tid].s, s_win[tid].b);
+            }
+        }
+        __syncthreads();
+        Bcur = K;
+        cur ^= 1;
+    }
+    // ---- CTA 0 hands the final state back (irec_beam_state_finish reads it) ----
+    if (blockIdx.x == 0) {
+        float* gb = st_beams(a.state, cur, B, DP);
+        for (int i = tid; i < B * DP; i += nt) gb[i] = s_beams[(size_t)cur * BMAX * DP + i];
+        if (tid == 0) { hdr->cur = cur; hdr->Bcur = Bcur; }
+    }
+}
+
 // raw stream (tests)
 __global__ void k_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out)
 {
@@ -1177,6 +1473,26 @@ static int launch_gp_score(int bmax, const ScoreArgs& a, int grid, size_t smem, 
     return IREC_E_INVALID;
 }
 
+static size_t fused_smem(int DP, int bmax, int cap)
+{
+    return sizeof(float) * ((size_t)IREC_T2_LEN + 8 * (size_t)DP + 2 * (size_t)bmax * DP + cap + GP2_THREADS + 32 + 1) +
+           sizeof(int32_t) * ((size_t)cap + 32 + TOPK_CAP + 4 + 1 + 2 + 32 + 64) + sizeof(irec_record_t) * 32 + 64;
+}
+template <int BMAX>
+static int launch_fused_t(const FusedArgs& a, int grid, size_t smem, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(k_gp_fused<BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)irec_device().max_smem_optin) != cudaSuccess)
+            return IREC_E_CUDA;
+        attr_done = true;
+    }
+    void* args[] = { const_cast<FusedArgs*>(&a) };
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_gp_fused<BMAX>), dim3(grid), dim3(GP2_THREADS), args, smem, s) != cudaSuccess)
+        return IREC_E_CUDA;
+    irec_count_launch();
+    return IREC_OK;
+}
 extern "C" {
 
 int irec_beam_uniform_int(int64_t q, int64_t start, int64_t n, int32_t* out, void* stream)
@@ -1380,8 +1696,6 @@ int irec_topb_merge(const irec_record_t* records, int n_records, int Bcur, int B
 //   [64 .. 64+world)  flag[sender] = last sequence number `sender` has pushed here
 //   [128 ..)          slot[parity][sender][(B + 1) * 4]   (parity = sequence & 1: a fast sender's next step never lands
 //                     in the slot its peers are still reading)
-#define P2P_FLAG_OFF 64
-#define P2P_SLOT_OFF 128
 __global__ void __launch_bounds__(256) k_p2p_exchange(int32_t* const* __restrict__ peer_bufs, int rank, int world, int B,
                                                        const int32_t* __restrict__ local, int32_t* __restrict__ out_records,
                                                        int32_t* __restrict__ out_counts)
@@ -1432,6 +1746,71 @@ int irec_p2p_exchange(void* const* peer_bufs, int rank, int world, int B, const 
                                                         reinterpret_cast<int32_t*>(out_records), out_counts);
     irec_count_launch();
     return irec_check_launch("k_p2p_exchange");
+}
+
+// ---------------- fused per-block launch (all auxiliary variables, grid + ranks) ------------------------
+int irec_beam_fused_fits(int D, int B)
+{
+    if (irec_init() != IREC_OK) return 0;
+    const int bmax = pick_bmax(B);
+    if (bmax < 0 || D <= 0 || D > 1024) return 0;
+    return fused_smem(make_geom(D).DP, bmax, gp2_cand_cap(D, bmax)) <= (size_t)irec_device().max_smem_optin ? 1 : 0;
+}
+size_t irec_beam_fused_workspace_bytes(int B, int world)
+{
+    if (irec_init() != IREC_OK) return 0;
+    const size_t grid = (size_t)irec_device().sm_count;
+    return 256 + sizeof(irec_record_t) * (grid * 32 + 64) + sizeof(int32_t) * (grid + 8) +
+           (sizeof(float) + sizeof(int32_t)) * ((grid + (size_t)std::max(world, 1)) * 32 + 64) + 64 + 0 * (size_t)B;
+}
+/* All auxiliary variables of the coder-block in `state` (after irec_beam_state_init) in one cooperative launch: this rank
+ * scores candidates [s_begin, s_end), the ranks' top-B lists are exchanged through peer_bufs (as irec_p2p_exchange; NULL
+ * and world = 1 on a single GPU).  Then irec_beam_state_finish.  IREC_E_CAPACITY: the block does not fit the fused kernel
+ * (D > 256 at 20 beams) -- use irec_beam_step_score / irec_beam_step_commit. */
+int irec_beam_encode_fused(void* state, int D, int B, int64_t s_begin, int64_t s_end, void* const* peer_bufs, int rank, int world,
+                           void* workspace, size_t workspace_bytes, void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    const int bmax = pick_bmax(B);
+    if (bmax < 0 || D <= 0) return irec_fail(IREC_E_INVALID, "beam_encode_fused: bad sizes");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && !peer_bufs))
+        return irec_fail(IREC_E_INVALID, "beam_encode_fused: bad rank / world / peer buffers");
+    if (workspace_bytes < irec_beam_fused_workspace_bytes(B, world)) return irec_fail(IREC_E_CAPACITY, "beam_encode_fused: workspace too small");
+    const BeamGeom g = make_geom(D);
+    if (D > 1024) return irec_fail(IREC_E_CAPACITY, "beam_encode_fused: D > 1024");
+    const int cap = gp2_cand_cap(D, bmax);
+    const size_t smem = fused_smem(g.DP, bmax, cap);
+    if (smem > (size_t)irec_device().max_smem_optin) return irec_fail(IREC_E_CAPACITY, "beam_encode_fused: block state does not fit shared memory");
+    const int64_t ns = s_end > s_begin ? s_end - s_begin : 0;
+    const int grid = gp2_score_grid(D, ns);
+    const size_t gsz = (size_t)irec_device().sm_count;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    FusedArgs a;
+    a.state = state; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4; a.ratio_tab = irec_ratio_tab();
+    a.s_begin = s_begin; a.s_end = s_end;
+    a.sync = reinterpret_cast<int32_t*>(w);
+    a.lists = reinterpret_cast<irec_record_t*>(w + 256);
+    a.win = a.lists + gsz * 32;
+    a.list_cnt = reinterpret_cast<int32_t*>(a.win + 64);
+    a.nwin = a.list_cnt + gsz;
+    a.g_sc = reinterpret_cast<float*>(a.nwin + 8);
+    a.g_id = reinterpret_cast<int32_t*>(a.g_sc + (gsz + (size_t)world) * 32 + 64);
+    a.peer_bufs = reinterpret_cast<int32_t* const*>(peer_bufs); a.rank = rank; a.world = world; a.cand_cap = cap;
+    if (cudaMemsetAsync(a.sync, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode_fused: memset failed");
+    int rc = IREC_E_INVALID;
+    switch (bmax) {
+        case 1: rc = launch_fused_t<1>(a, grid, smem, s); break;
+        case 2: rc = launch_fused_t<2>(a, grid, smem, s); break;
+        case 4: rc = launch_fused_t<4>(a, grid, smem, s); break;
+        case 8: rc = launch_fused_t<8>(a, grid, smem, s); break;
+        case 10: rc = launch_fused_t<10>(a, grid, smem, s); break;
+        case 16: rc = launch_fused_t<16>(a, grid, smem, s); break;
+        case 20: rc = launch_fused_t<20>(a, grid, smem, s); break;
+        case 32: rc = launch_fused_t<32>(a, grid, smem, s); break;
+    }
+    if (rc != IREC_OK) { cudaGetLastError(); return irec_fail(rc, "beam_encode_fused: cooperative launch failed"); }
+    return irec_check_launch("k_gp_fused");
 }
 
 // ---------------- the block-batched entry point ------------------------------------------------

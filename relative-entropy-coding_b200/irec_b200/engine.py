@@ -461,7 +461,31 @@ class ShardedBeamBlock:
         graphs[n_aux].replay()
         return self.finish()
 
-    def finish(self):
+    def fused_available(self):
+        """the one-launch path needs the block state to fit shared memory (D <= 256 at 20 beams) and, across ranks, the
+        peer-memory exchange buffers"""
+        return bool(N.lib().irec_beam_fused_fits(self.D, self.B)) and (self.world == 1 or self.p2p is not None)
+
+    def encode_fused(self, t_loc, t_scale, p_loc, p_scale, seed):
+        """encode() as ONE cooperative launch for all auxiliary variables (irec_beam_encode_fused): per variable a single
+        all-to-all point inside the kernel instead of seven dependent launches; no host read of n_aux before the launch.
+        Falls back to the step loop where the fused kernel does not apply."""
+        if not self.fused_available():
+            return self.encode(t_loc, t_scale, p_loc, p_scale, seed)
+        lib = N.lib()
+        N.check(lib.irec_beam_state_init(N.ptr(self.state), N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale),
+                                         None, 0, self.D, self.omega, self.S, self.B, self.max_aux, int(seed),
+                                         N.stream_ptr()), "irec_beam_state_init")
+        if getattr(self, "_fused_ws", None) is None:
+            self._fused_ws = torch.empty(int(lib.irec_beam_fused_workspace_bytes(self.B, self.world)), dtype=torch.uint8,
+                                         device=self.device)
+        peers = N.ptr(self.p2p["ptrs"]) if self.p2p is not None else None
+        N.check(lib.irec_beam_encode_fused(N.ptr(self.state), self.D, self.B, self.s_begin, self.s_end, peers, self.rank,
+                                           self.world, N.ptr(self._fused_ws), self._fused_ws.numel(), N.stream_ptr()),
+                "irec_beam_encode_fused")
+        return self.finish(read_n_aux=True)
+
+    def finish(self, read_n_aux=False):
         lib = N.lib()
         idx = torch.zeros(self.max_aux, dtype=torch.int32, device=self.device)
         meta = torch.zeros(2, dtype=torch.int32, device=self.device)
@@ -469,6 +493,12 @@ class ShardedBeamBlock:
         N.check(lib.irec_beam_state_finish(N.ptr(self.state), self.D, None, 0, N.ptr(idx),
                                            C.c_void_p(meta.data_ptr()), C.c_void_p(meta.data_ptr() + 4), N.ptr(sample),
                                            N.stream_ptr()), "irec_beam_state_finish")
+        if read_n_aux:                      # n_aux / status were never read on the host: one D2H of (n_aux, status, indices)
+            host = torch.cat([meta, idx]).cpu()
+            self.n_aux, status = int(host[0]), int(host[1])
+            if status != N.BLK_OK:
+                raise CodingError(f"sharded beam encode: bad block (status {status}, n_aux {self.n_aux})")
+            return host[2:2 + self.n_aux].tolist(), sample
         return idx[:self.n_aux].tolist(), sample
 
     def encode(self, t_loc, t_scale, p_loc, p_scale, seed):

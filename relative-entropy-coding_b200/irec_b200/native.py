@@ -56,6 +56,9 @@ _SIGNATURES = {
     "irec_beam_step_commit": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "irec_beam_state_finish": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "irec_topb_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "irec_beam_fused_fits": (C.c_int, [_i32, _i32]),
+    "irec_beam_fused_workspace_bytes": (C.c_size_t, [_i32, _i32]),
+    "irec_beam_encode_fused": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp, _sz, _vp]),
     "irec_p2p_exchange_bytes": (C.c_size_t, [_i32, _i32]),
     "irec_p2p_exchange": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "irec_is_workspace_bytes": (C.c_size_t, [_i32]),

@@ -31,7 +31,15 @@ def main():
         idx, sample = blk.encode(*d, seed=seed)
         ref = O.beam_encode_block(mu, sig, pl, ps, omega, S, B, seed)
         same = idx == ref["indices"].tolist() and np.array_equal(sample.cpu().numpy().view(np.uint32), ref["sample"].view(np.uint32))
-        print(f"rank {rank}/{world} D={D} S={S} B={B} n_aux={len(idx)} range=[{blk.s_begin},{blk.s_end}) match={same}", flush=True)
+        # the one-launch path (irec_beam_encode_fused; peer-memory exchange inside the kernel) where it applies
+        fused = "n/a"
+        if blk.fused_available() and blk.world > 1:
+            for rep in range(2):           # twice: the exchange buffers' sequence numbers carry over
+                idx_f, sample_f = blk.encode_fused(*d, seed=seed)
+                fused = bool(idx_f == idx and torch.equal(sample_f, sample))
+                same = same and fused
+        print(f"rank {rank}/{world} D={D} S={S} B={B} n_aux={len(idx)} range=[{blk.s_begin},{blk.s_end}) match={same} "
+              f"fused={fused} exchange={'p2p' if blk.p2p is not None else 'nccl'}", flush=True)
         ok = ok and same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -283,6 +283,24 @@ def test_sharded_block_single_rank(cuda):
     assert np.array_equal(bits(sample.cpu().numpy()), bits(ref["sample"]))
 
 
+@pytest.mark.parametrize("D,S,B,seed", [(64, 2000, 10, 42), (64, 36, 20, 42), (200, 5000, 20, 7), (37, 300, 5, 1), (64, 7, 32, 3), (1, 50, 3, 5)])
+def test_fused_block_single_rank(cuda, D, S, B, seed):
+    """all auxiliary variables of a block in ONE cooperative launch (irec_beam_encode_fused: state replicas per CTA, last-arriver
+    merge of the grid's top-B lists) == oracle == the multi-launch state machine"""
+    from irec_b200 import engine
+    mu, sig, pl, ps = synth.c1(D, data_seed=D + S)
+    d = to_dev((mu, sig, pl, ps), cuda)
+    omega = np.float32(np.log(S) / 1.2)
+    blk = engine.ShardedBeamBlock(D, S, B, omega, max_aux=64, device=cuda)
+    assert blk.fused_available() == (B <= 20)            # 32 beams: the candidate buffer does not fit beside the table
+    idx, sample = blk.encode_fused(*d, seed=seed)        # (falls back to the step loop then)
+    ref = O.beam_encode_block(mu, sig, pl, ps, omega, S, B, seed)
+    assert idx == ref["indices"].tolist()
+    assert np.array_equal(bits(sample.cpu().numpy()), bits(ref["sample"]))
+    idx2, sample2 = blk.encode(*d, seed=seed)
+    assert idx2 == idx and np.array_equal(bits(sample2.cpu().numpy()), bits(sample.cpu().numpy()))
+
+
 def test_errors(cuda):
     from irec_b200 import Normal
     from rec.coding import BeamSearchCoder
