@@ -97,6 +97,15 @@ int irec_kl_naux(const float* t_loc, const float* t_scale, const float* p_loc, c
                  const int64_t* gather_idx, const int64_t* block_offsets, int nb, float omega,
                  float* out_kl, int32_t* out_n_aux, void* stream);
 
+/* KL, n_aux and the per-partition per-dim coefficients of ONE block of D contiguous dims -- the schedule both the encode
+ * and the decode kernels evaluate on the fly (rec/coding/beam_search_coder.py:57-77, coder.py:141-154): for auxiliary
+ * variable t and dim d, sa = sqrt(v_t) (scale of the candidates), M = mean of the auxiliary target, and the centred
+ * quadratic log-weight coefficients A = (1/tot - 1/s2) / 2, E = M / tot.  Outputs [max_aux x D] row-major, rows t < n_aux
+ * written; nothing is written when n_aux is invalid (check out_n_aux: <= 0, > max_aux, beyond the ratio table). */
+int irec_schedule(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale, int D, float omega,
+                  int max_aux, float* out_kl, int32_t* out_n_aux, float* out_sa, float* out_A, float* out_E, float* out_M,
+                  void* stream);
+
 /* ---- beam-search coder (rec/coding/beam_search_coder.py) ------------------------------------ */
 
 /* bytes of device workspace irec_beam_encode needs for these sizes */

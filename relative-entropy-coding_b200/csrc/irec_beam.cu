@@ -896,36 +896,40 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
         const float4* beams4 = reinterpret_cast<const float4*>(s_beams + (size_t)cur * BMAX * DP);
         const TfStream st = tf_stream_seeded(seed + t, seed + t);
 
-        // ---- score this CTA's sample groups, keep its best B (as k_gp_score_topb2) ----
+        // ---- score this CTA's sample groups, keep its best B (as k_gp_score_topb2).  A warp whose first group of a round lies
+        //      beyond the CTA's range only joins the barriers: with a GPU's share of ~30 groups per CTA (S = 6e5 over 8 GPUs)
+        //      a round of clamped duplicates would double the work ----
         for (int64_t base = sg0; base < sg1; base += (int64_t)nwarps * GP2_NS) {
-            uint64_t jb[GP2_NS];
-            uint32_t row[GP2_NS];
-#pragma unroll
-            for (int k = 0; k < GP2_NS; ++k) {
-                const int64_t s = a.s_begin + (base + warp + (int64_t)k * nwarps) * g.SPW + lane / g.P;
-                const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // groups beyond the range: clamped, not stored
-                jb[k] = s_eff * (uint64_t)g.D + (uint64_t)(32 * lg);
-                row[k] = 0u;
-            }
-            const int s_first = (int)(a.s_begin + (base + warp) * g.SPW + lane / g.P);
             const float tau = *s_tau;
+            if (base + warp < sg1) {
+                uint64_t jb[GP2_NS];
+                uint32_t row[GP2_NS];
+#pragma unroll
+                for (int k = 0; k < GP2_NS; ++k) {
+                    const int64_t s = a.s_begin + (base + warp + (int64_t)k * nwarps) * g.SPW + lane / g.P;
+                    const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // groups beyond the range: clamped, not stored
+                    jb[k] = s_eff * (uint64_t)g.D + (uint64_t)(32 * lg);
+                    row[k] = 0u;
+                }
+                const int s_first = (int)(a.s_begin + (base + warp) * g.SPW + lane / g.P);
 #pragma unroll 1
-            for (int boff = 0; boff < BMAX; boff += HB) {
-                if (boff >= Bcur) break;
-                float acc[GP2_NS][HB];
+                for (int boff = 0; boff < BMAX; boff += HB) {
+                    if (boff >= Bcur) break;
+                    float acc[GP2_NS][HB];
 #pragma unroll
-                for (int k = 0; k < GP2_NS; ++k)
+                    for (int k = 0; k < GP2_NS; ++k)
 #pragma unroll
-                    for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
-                r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
-                                                        g.P, lg, st, jb, nullptr, row, acc);
-                float v[GP2_NS * HB];
+                        for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
+                    r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
+                                                            g.P, lg, st, jb, nullptr, row, acc);
+                    float v[GP2_NS * HB];
 #pragma unroll
-                for (int k = 0; k < GP2_NS; ++k)
+                    for (int k = 0; k < GP2_NS; ++k)
 #pragma unroll
-                    for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
-                const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, s_hi };
-                r2_tree_store<GP2_NS * HB, GP2_NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
+                        for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
+                    const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, s_hi };
+                    r2_tree_store<GP2_NS * HB, GP2_NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
+                }
             }
             __syncthreads();
             const int cnt = *s_cnt;
@@ -960,17 +964,20 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             // rank top-B over the grid's lists
             if (tid == 0) *s_cnt = 0;
             __syncthreads();
+            // merge scratch: the CTA's own candidate buffer (free at this point) when the lists fit, else global memory
+            float* m_sc = ((int)gridDim.x * B <= cap && a.world * B <= cap) ? s_csc : a.g_sc;
+            int32_t* m_id = (m_sc == s_csc) ? s_cid : a.g_id;
             for (int i = tid; i < (int)gridDim.x * B; i += nt) {
                 const int li = i / B, e = i - li * B;
                 if (e < __ldcg(a.list_cnt + li)) {
                     const int pos = atomicAdd(s_cnt, 1);
                     const int4 v = __ldcg(reinterpret_cast<const int4*>(a.lists) + i);      // (score bits, s, b, pad) straight from L2
-                    a.g_sc[pos] = __int_as_float(v.x);
-                    a.g_id[pos] = v.y * Bcur + v.z;
+                    m_sc[pos] = __int_as_float(v.x);
+                    m_id[pos] = v.y * Bcur + v.z;
                 }
             }
             __syncthreads();
-            int K = block_topk(a.g_sc, a.g_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+            int K = block_topk(m_sc, m_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
             if (a.world > 1) {
                 // exchange the rank lists over peer memory (protocol of k_p2p_exchange), then merge the world's lists
                 int32_t* mine = a.peer_bufs[a.rank];
@@ -1009,12 +1016,12 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
                     const int r = i / B, e = i - r * B;
                     if (e < slots[r * W + B * 4]) {
                         const int pos = atomicAdd(s_cnt, 1);
-                        a.g_sc[pos] = __int_as_float(slots[r * W + e * 4]);
-                        a.g_id[pos] = slots[r * W + e * 4 + 1] * Bcur + slots[r * W + e * 4 + 2];
+                        m_sc[pos] = __int_as_float(slots[r * W + e * 4]);
+                        m_id[pos] = slots[r * W + e * 4 + 1] * Bcur + slots[r * W + e * 4 + 2];
                     }
                 }
                 __syncthreads();
-                K = block_topk(a.g_sc, a.g_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
+                K = block_topk(m_sc, m_id, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
                 if (tid == 0) mine[0] = seq;
             }
             if (tid < K) {
@@ -1082,6 +1089,30 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
         float* gb = st_beams(a.state, cur, B, DP);
         for (int i = tid; i < B * DP; i += nt) gb[i] = s_beams[(size_t)cur * BMAX * DP + i];
         if (tid == 0) { hdr->cur = cur; hdr->Bcur = Bcur; }
+    }
+}
+
+// schedule export (include/irec.h: irec_schedule): per-partition per-dim coefficients of ONE block, exactly what the encode
+// kernels compute on the fly (beam_sched_dim); thread d walks the auxiliary variables of its dim
+__global__ void k_schedule(const float* __restrict__ t_loc, const float* __restrict__ t_scale, const float* __restrict__ p_loc,
+                           const float* __restrict__ p_scale, int D, int max_aux, const int32_t* __restrict__ n_aux_ptr,
+                           const float* __restrict__ ratio_tab, int ratio_len, float* __restrict__ out_sa, float* __restrict__ out_A,
+                           float* __restrict__ out_E, float* __restrict__ out_M)
+{
+    const int n_aux = *n_aux_ptr;
+    if (n_aux <= 0 || n_aux > max_aux || n_aux > ratio_len) return;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+        const float ps = p_scale[d], ts = t_scale[d];
+        const float cv = __fmul_rn(ps, ps), tv = __fmul_rn(ts, ts), dmu = __fadd_rn(t_loc[d], -p_loc[d]);
+        float cum = 0.f;
+        for (int t = 0; t < n_aux; ++t) {
+            SchedOut o;
+            o.sa = 0.f; o.A = 0.f; o.E = 0.f; o.M = 0.f; o.cum_next = cum;
+            if (cv != 0.f) o = beam_sched_dim(cv, tv, dmu, cum, ratio_tab[n_aux - 1 - t]);
+            out_sa[(size_t)t * D + d] = o.sa; out_A[(size_t)t * D + d] = o.A;
+            out_E[(size_t)t * D + d] = o.E; out_M[(size_t)t * D + d] = o.M;
+            cum = o.cum_next;
+        }
     }
 }
 
@@ -1526,6 +1557,31 @@ int irec_kl_naux(const float* t_loc, const float* t_scale, const float* p_loc, c
         t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, out_kl, out_n_aux);
     irec_count_launch();
     return irec_check_launch("k_kl_naux");
+}
+
+/* KL, n_aux and the per-partition per-dim schedule of one block of D contiguous dims (beam_search_coder.py:57-77;
+ * coder.py:141-154): out_sa / out_A / out_E / out_M are [max_aux x D], rows t < n_aux are written (none when n_aux is
+ * invalid: <= 0, > max_aux or beyond the ratio table -- check out_n_aux). */
+int irec_schedule(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale, int D, float omega,
+                  int max_aux, float* out_kl, int32_t* out_n_aux, float* out_sa, float* out_A, float* out_E, float* out_M,
+                  void* stream)
+{
+    IREC_ENSURE_INIT();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D <= 0 || max_aux <= 0 || !out_n_aux) return irec_fail(IREC_E_INVALID, "irec_schedule: bad arguments");
+    if (((D + 31) >> 5) > KL_MAX_CHUNKS) return irec_fail(IREC_E_CAPACITY, "irec_schedule: D too large (max 131072 per block)");
+    if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "irec_schedule: kl_per_partition must be > 0");
+    int64_t h_offs[2] = { 0, D };
+    int64_t* d_offs = nullptr;      // two offsets: small pooled allocation, stream-ordered
+    if (cudaMallocAsync(&d_offs, sizeof(h_offs), s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "irec_schedule: allocation failed");
+    cudaMemcpyAsync(d_offs, h_offs, sizeof(h_offs), cudaMemcpyHostToDevice, s);
+    k_kl_naux<<<1, 256, 0, s>>>(t_loc, t_scale, p_loc, p_scale, nullptr, d_offs, 1, omega, out_kl, out_n_aux);
+    irec_count_launch();
+    k_schedule<<<std::max(1, std::min((D + 127) / 128, 1024)), 128, 0, s>>>(t_loc, t_scale, p_loc, p_scale, D, max_aux, out_n_aux,
+                                                                             irec_ratio_tab(), irec_ratio_len(), out_sa, out_A, out_E, out_M);
+    irec_count_launch();
+    cudaFreeAsync(d_offs, s);
+    return irec_check_launch("irec_schedule");
 }
 
 int irec_beam_decode(const float* p_loc, const float* p_scale, const int64_t* gather_idx,

@@ -49,6 +49,22 @@ def kl_naux(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega
     return kl, na
 
 
+def schedule(t_loc, t_scale, p_loc, p_scale, omega, max_aux=4096):
+    """(kl, n_aux, sa, A, E, M) of one block: the per-partition per-dim coefficients the kernels evaluate on the fly
+    (include/irec.h: irec_schedule); sa/A/E/M are [n_aux, D] device tensors.  Diagnostics / tests: reads n_aux back."""
+    dev = t_loc.device
+    D = t_loc.numel()
+    kl = torch.empty(1, dtype=torch.float32, device=dev)
+    na = torch.empty(1, dtype=torch.int32, device=dev)
+    outs = [torch.zeros((max_aux, D), dtype=torch.float32, device=dev) for _ in range(4)]
+    N.check(N.lib().irec_schedule(N.ptr(t_loc), N.ptr(t_scale), N.ptr(p_loc), N.ptr(p_scale), D, float(omega), int(max_aux),
+                                  N.ptr(kl), N.ptr(na), *(N.ptr(o) for o in outs), N.stream_ptr()), "irec_schedule")
+    n = int(na.cpu()[0])
+    if n <= 0 or n > max_aux:
+        raise CodingError(f"schedule: KL divergence is not finite, zero, or needs more than {max_aux} auxiliary variables (n_aux={n})")
+    return float(kl.cpu()[0]), n, *(o[:n] for o in outs)
+
+
 def _raise_status(status, n_aux, what):
     if not bool((status != N.BLK_OK).any()):
         return

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "irec_bm_components_host": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "irec_uniform_int_stream": (C.c_int, [_i64, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
     "irec_kl_naux": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp]),
+    "irec_schedule": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "irec_beam_encode_workspace_bytes": (C.c_size_t, [_i32, _i64, _i32, _i32, _i32]),
     "irec_beam_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _i32, _i32, _i64,
                                    _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -34,6 +34,24 @@ class BeamSearchCoder(GaussianCoder):
         w = torch.arange(69, 69 + m.shape[1], dtype=torch.int32)
         return torch.remainder((m * w).sum(dim=1, dtype=torch.int32), self.big_prime - 1) + 1
 
+    def get_pseudo_random_sample(self, dist, n_samples, index_matrix, seed):
+        """reference :37-51: the [n_samples, n_beams', D] candidate tensor  quantile((r * h) mod 10007 / 10007) * scale  with
+        r = the seeded uniform-int stream and h = simple_hash(index_matrix).  The kernels never materialise it (they gather
+        the same table values inside the scoring loop); kept for API parity and for inspection.  `dist` needs `.scale`
+        ([1, D] or [D]); returns a float32 CUDA tensor, bit-identical to what the kernels score."""
+        scale = E._f32c(dist.scale, "cuda").reshape(-1)
+        D = scale.numel()
+        r = E.beam_uniform_int(int(seed), 0, int(n_samples) * D, device=scale.device).to(torch.int64).reshape(int(n_samples), 1, D)
+        h = self.simple_hash(index_matrix).to(device=scale.device, dtype=torch.int64).reshape(1, -1, 1)
+        k = torch.remainder(r * h, self.big_prime)
+        T = self.__dict__.get("_ndtri_dev")
+        if T is None or T.device != scale.device:
+            from irec_b200 import native as N
+            T = self.__dict__["_ndtri_dev"] = N.ndtri_table().to(scale.device)
+        out = T[k] * scale.reshape(1, 1, D)
+        loc = getattr(dist, "loc", None)
+        return out if loc is None else out + E._f32c(loc, "cuda").reshape(1, 1, D)      # quantile(p) = ndtri(p) * scale + loc
+
     def _encode_flat(self, tl, ts, pl, ps, gather, offsets, nb, max_dim, seed):
         with self._ratios_ctx(tl.device):
             res = E.beam_encode_blocks(tl, ts, pl, ps, gather, offsets, nb, max_dim, self.kl_per_partition, self.n_samples,

@@ -11,7 +11,8 @@ coder-blocks instead of a Python loop, and the `print`s of the reference are gon
 Learned auxiliary ratios (`extrapolate_auxiliary_ratios=False`, reference coder.py:197-410) are
 calibrated by `update_auxiliary_variance_ratios` (an offline SGD fit, torch autograd on the tensors' device) and then
 handed to the kernels as a device table (include/irec.h: irec_set_thread_aux_ratios) in place of the power law.
-Out of scope: the rejection sampler (its acceptance test draws unseeded uniforms, reference rejection_sampling.py:86-87).
+The rejection sampler (rec/coding/rejection_sampling.py, samplers.py) is host logic over GPU-regenerated candidate streams; its
+two unseeded draws in the reference are seeded here.
 """
 import abc
 

@@ -14,6 +14,9 @@ class _Header(C.Structure):
                 ("uses_index_counts_file", C.c_uint16), ("n_res_blocks", C.c_int32)]
 
 
+MAX_INDEX_LIMIT = 1 << 28      # alphabet of the arithmetic coder (the reference's examples use max_index = 20)
+
+
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
@@ -44,6 +47,9 @@ def write_compressed_code(file_path,
         index_counts = np.ascontiguousarray(np.load(index_counts_file), dtype=np.int64)
         if index_counts.size != max_index + 1:
             raise ValueError("index counts must have max_index + 1 entries")
+    if len(block_indices) > 0xFFFF:
+        # the container stores the number of residual blocks as uint16; the reference's struct.pack raises here too
+        raise ValueError(f"too many residual blocks for the .rec container: {len(block_indices)} > 65535")
     h = _Header(int(seed), int(block_size), int(max_index), img_h, img_w, img_c, 0, 0, len(block_indices))
     n = C.c_int64(0)
     N.check(N.load_library().irec_rec_write_file(str(file_path).encode(), C.byref(h), _ptr(num_blocks), _ptr(num_aux),
@@ -63,9 +69,13 @@ def read_compressed_code(file_path,
     N.check(lib.irec_rec_read_header(_ptr(data), int(data.size), C.byref(h)), "irec_rec_read_header")
     if h.uses_index_counts_file and index_counts_file is None:
         raise ValueError("The compressed file is using empirical index counts, but no counts file was supplied!")
+    if h.max_index >= MAX_INDEX_LIMIT:
+        raise ValueError(f"corrupt .rec header: max_index {h.max_index} (limit {MAX_INDEX_LIMIT})")
     index_counts = None
     if h.uses_index_counts_file:
         index_counts = np.ascontiguousarray(np.load(index_counts_file), dtype=np.int64)
+        if index_counts.size != h.max_index + 1:     # the decoder reads max_index + 1 counts
+            raise ValueError(f"index counts file has {index_counts.size} entries, the header needs {h.max_index + 1}")
     num_blocks = np.zeros(max(1, h.n_res_blocks), dtype=np.int32)
     cap_a, cap_i = 1024, 16384
     while True:

@@ -20,25 +20,27 @@ def cuda(built):
     return "cuda:0"
 
 
-def test_rvae_compress_decompress(cuda):
-    """configs[1] shape: 32x32 image, every level a [1,16,16,32] latent, block_size 1000, beam search B=20, 1+eps=1.2"""
+@pytest.mark.parametrize("num_res_blocks", [6, 24])
+def test_rvae_compress_decompress(cuda, num_res_blocks):
+    """configs[1] shape: 32x32 image, every level a [1,16,16,32] latent, block_size 1000, beam search B=20, 1+eps=1.2;
+    24 residual blocks = the configuration BASELINE.json names (resnet_vae.py:803-836), 6 = the quick variant"""
     import torch
     from rec.models import BidirectionalResNetVAE
     torch.manual_seed(0)
-    model = BidirectionalResNetVAE(num_res_blocks=6, sampler="beam_search",
+    model = BidirectionalResNetVAE(num_res_blocks=num_res_blocks, sampler="beam_search",
                                    sampler_args={"n_beams": 20, "extra_samples": 1.2}, coder_args={"block_size": 1000},
                                    deterministic_filters=64, stochastic_filters=32, kl_per_partition=3.).to(cuda)
     image = (torch.rand(1, 32, 32, 3, device=cuda) - 0.5)
     model(image)                                     # data-dependent initialisation pass (reference: first call)
     model(image)
     block_indices, reconstruction = model.compress(image, seed=42)
-    assert len(block_indices) == 6 and all(len(level) == 9 for level in block_indices)        # 8 x 1000 + 192 dims
+    assert len(block_indices) == num_res_blocks and all(len(level) == 9 for level in block_indices)        # 8 x 1000 + 192 dims
     assert all(isinstance(i, int) and 0 <= i < 36 for level in block_indices for blk in level for i in blk)
     enc_latent_priors = [(blk.prior.loc.clone(), blk.prior.scale.clone()) for blk in model.residual_blocks]
     # reference quirk kept: the model hands every level's LIST OF BLOCKS to coder.get_codelength (resnet_vae.py:838-842),
     # whose beam-search version is len(.) * ln S (beam_search_coder.py:150-151) -- blocks, not auxiliary variables
     nats = model.get_codelength(block_indices)
-    assert np.isclose(nats, 6 * 9 * np.log(36))
+    assert np.isclose(nats, num_res_blocks * 9 * np.log(36))
     per_block = sum(model.residual_blocks[0].coder.get_codelength(blk) for level in block_indices for blk in level)
     assert np.isclose(per_block, sum(len(blk) for level in block_indices for blk in level) * np.log(36))
     decoded = model.decompress([[list(b) for b in level] for level in block_indices], seed=42, height=32, width=32)

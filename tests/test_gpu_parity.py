@@ -580,3 +580,28 @@ def test_encode_grows_row_capacity_without_presizing(cuda):
     E._aux_hint.clear()
     get, s3 = coder.encode_batch(t, p, seed=3, lazy=True)
     assert get()[0] == idx1 and torch.equal(s3.reshape(-1), s1.reshape(-1))
+
+
+def test_schedule_export_and_pseudo_random_sample(cuda):
+    """irec_schedule == the oracle's schedule bit for bit, and BeamSearchCoder.get_pseudo_random_sample
+    (reference beam_search_coder.py:37-51) == the reference-structured port's candidate tensor"""
+    import torch
+    from irec_b200 import Normal, engine as E
+    from oracle import ref_numpy as R
+    from rec.coding import BeamSearchCoder
+    for recipe, D in (("c2", 1000), ("c3", 288), ("c1", 64), ("c2", 37)):
+        tl, ts, pl, ps = getattr(synth, recipe)(D, data_seed=4)
+        d = to_dev((tl, ts, pl, ps), cuda)
+        kl, n, sa, A, Ec, M = E.schedule(*d, 3.0)
+        okl = O.kl(tl, ts, pl, ps)
+        assert bits(np.float32(kl)) == bits(np.float32(okl)) and n == O.n_aux(okl, 3.0)
+        osa, oA, oE, oM = O.beam_schedule(tl, ts, pl, ps, n)
+        for got, ref in ((sa, osa), (A, oA), (Ec, oE), (M, oM)):
+            assert np.array_equal(bits(got.cpu().numpy()), bits(np.asarray(ref, np.float32).reshape(n, D)))
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2)
+    scale = np.exp(np.random.default_rng(1).uniform(-1, 0, 50)).astype(np.float32)
+    idx = np.array([[3, 5], [7, 1], [0, 35]], np.int32)
+    got = coder.get_pseudo_random_sample(Normal(np.zeros((1, 50), np.float32), scale[None, :], device=cuda), coder.n_samples, idx, 43)
+    ref = R._pseudo_random_sample(scale, coder.n_samples, idx, 43)
+    assert got.shape == (36, 3, 50)
+    assert np.array_equal(bits(got.cpu().numpy()), bits(ref))
