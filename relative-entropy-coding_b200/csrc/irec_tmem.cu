@@ -542,6 +542,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                 for (int i = tid; i < g.DP; i += nt) s_M[i] = s_next[3 * DPm + i];
                 if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
                 tm_wait_st();
+                // every serial warp has read NEXT: the context's next compute_next may overwrite it (it follows at once when the
+                // other context has retired -- found by compute-sanitizer racecheck, profiles/r2b_sanitizer_racecheck.log)
+                ser_sync();
             };
 
             if (B_.active) {

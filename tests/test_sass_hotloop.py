@@ -79,3 +79,62 @@ def test_quantile_gathers_stay_software_pipelined(built):
     dist, local = hot[0]
     assert statistics.median(dist) >= 10, (statistics.median(dist), sorted(dist)[:10])
     assert local <= 4, local
+
+
+def _tmem_kernel_sass(tmp):
+    subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True, check=True)
+    cub = [f for f in os.listdir(tmp) if f.startswith("irec_tmem.")][0]
+    dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True, check=True).stdout
+    out, on, cur = [], False, None
+    for ln in dis.splitlines():
+        if ln.startswith(".text."):
+            on = "k_beam_encode_tmemILi20E" in ln
+            continue
+        if not on:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = int(m.group(2)) if m.group(1).endswith("irec_tmem.cu") else -1
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)
+        if m:
+            out.append((cur, m.group(1).strip()))
+    return out
+
+
+def test_tmem_kernel_hot_loop(built):
+    """k_beam_encode_tmem<20> (the default batch kernel): the scoring loop reads its beams / coefficients with tensor-memory
+    loads (LDTM), keeps the quantile gathers software-pipelined (median gather -> use distance >= 10 instructions) and does
+    not touch local memory; the kernel allocates tensor memory (UTCATOMSWS / tcgen05.alloc) and stores to it (STTM)."""
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")):
+        pytest.skip("CUDA binary utilities not available")
+    src = open(os.path.join(ROOT, "relative-entropy-coding_b200", "csrc", "irec_tmem.cu")).read().splitlines()
+    gather_line = 1 + next(i for i, l in enumerate(src) if "tv[g][e] = *reinterpret_cast<const float*>(T2b + (ad[k][e] + cb[b0 + g]));" in l)
+    with tempfile.TemporaryDirectory() as tmp:
+        ins = _tmem_kernel_sass(tmp)
+    assert any(t.startswith("LDTM") for _, t in ins) and any(t.startswith("STTM") for _, t in ins)
+    idx = [i for i, (c, t) in enumerate(ins) if c == gather_line and re.match(r"LDS R\d+", t)]
+    assert idx
+    groups, g = [], [idx[0]]
+    for a, b in zip(idx, idx[1:]):
+        if b - a > 400:
+            groups.append(g)
+            g = []
+        g.append(b)
+    groups.append(g)
+    hot = max(groups, key=len)                       # the main scoring rounds: 4 sample groups x 5 beams x 4 dims = 80 gathers per quad
+    assert len(hot) >= 60, [len(x) for x in groups]
+    body = ins[hot[0]:hot[-1] + 1]
+    assert not any(re.match(r"(LDL|STL)", t) for _, t in body)
+    around = ins[max(0, hot[0] - 120):hot[-1] + 120]
+    assert sum(1 for _, t in around if t.startswith("LDTM")) >= 8          # 3 coefficient quads + 5 beam quads per quad of dims
+    dist = []
+    for k in hot:
+        m = re.match(r"LDS R(\d+),", ins[k][1])
+        reg = re.compile(r"\bR" + m.group(1) + r"\b")
+        for n in range(k + 1, min(k + 600, len(ins))):
+            ops = ins[n][1].split(",", 1)
+            if len(ops) > 1 and reg.search(ops[1]):
+                dist.append(n - k)
+                break
+    assert statistics.median(dist) >= 10, statistics.median(dist)
