@@ -49,7 +49,7 @@
 #define TM_HB 5                    // beams per quarter and context
 #define TM_COLS 512
 #ifndef TM_NSBIG
-#define TM_NSBIG 4                 // sample groups per warp and round in the main scoring rounds
+#define TM_NSBIG 3                 // sample groups per warp and round in the main scoring rounds
 #endif
 #define TM_COEF_COL0 320           // first coefficient column (after 2 contexts x 5 beams x 32 dims)
 
@@ -102,6 +102,17 @@ __device__ __forceinline__ void tm_tie16(float (&r)[16])
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic of sm_100 (SASS FMUL2 / FADD2 / FFMA2): one warp-instruction, two IEEE round-to-nearest float32
+// operations on an aligned register pair -- the same bits as two scalar instructions, half the issue slots.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// ---------------------------------------------------------------------------------------------
 // Chunk sums of NS candidate samples against the HB beams of this warp's half.  Same float32 operation order per
 // candidate-dim as r2_score_chunk / the oracle (beam_score):  x = beam + T2[a + c_b] * sigma_aux;  d = x - M;
 // acc = fma(fma(A, d, E), d, acc).   tm_beams / tm_coef: TMEM addresses (quarter lane base + first column).
@@ -147,12 +158,17 @@ __device__ __forceinline__ void tm_score_chunk(const char* __restrict__ T2b, uin
         float bm[HB][4];
 #pragma unroll
         for (int b = 0; b < HB; ++b) tm_ld4(tm_beams + 32 * b + 4 * iq, bm[b]);
-        const float4 Mq = M4[iq * P + lg];
-        const float M[4] = { Mq.x, Mq.y, Mq.z, Mq.w };
+        const float4 nMq = M4[iq * P + lg];           // shared memory holds -M (x - M == x + (-M) bit for bit)
         tm_wait_ld();
         tm_tie4(sa); tm_tie4(A); tm_tie4(E);
 #pragma unroll
         for (int b = 0; b < HB; ++b) tm_tie4(bm[b]);
+        // dims (0,1) and (2,3) of the quad as packed pairs: v = T*sa, x = beam + v, d = x - M, t = fma(A, d, E) are four packed
+        // instructions per pair; the accumulation a = fma(t, d, a) stays scalar and sequential in d (the canonical order)
+        const f32x2_t sa2[2] = { f2_pack(sa[0], sa[1]), f2_pack(sa[2], sa[3]) };
+        const f32x2_t A2[2] = { f2_pack(A[0], A[1]), f2_pack(A[2], A[3]) };
+        const f32x2_t E2[2] = { f2_pack(E[0], E[1]), f2_pack(E[2], E[3]) };
+        const f32x2_t nM2[2] = { f2_pack(nMq.x, nMq.y), f2_pack(nMq.z, nMq.w) };
 #pragma unroll
         for (int b0 = 0; b0 < HB; b0 += G) {
 #pragma unroll
@@ -168,11 +184,16 @@ __device__ __forceinline__ void tm_score_chunk(const char* __restrict__ T2b, uin
                 for (int g = 0; g < G; ++g) {
                     float a = acc[k][b0 + g];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x = __fadd_rn(bm[b0 + g][e], __fmul_rn(tv[g][e], sa[e]));
-                        const float d = __fadd_rn(x, -M[e]);
-                        const float t = __fmaf_rn(A[e], d, E[e]);
-                        a = __fmaf_rn(t, d, a);
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const f32x2_t x = f2_add(f2_pack(bm[b0 + g][2 * h2], bm[b0 + g][2 * h2 + 1]),
+                                                 f2_mul(f2_pack(tv[g][2 * h2], tv[g][2 * h2 + 1]), sa2[h2]));
+                        const f32x2_t d = f2_add(x, nM2[h2]);
+                        const f32x2_t t = f2_fma(A2[h2], d, E2[h2]);
+                        float d0, d1, t0, t1;
+                        f2_unpack(d, d0, d1);
+                        f2_unpack(t, t0, t1);
+                        a = __fmaf_rn(t0, d0, a);
+                        a = __fmaf_rn(t1, d1, a);
                     }
                     acc[k][b0 + g] = a;
                 }
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
     unsigned char* ser_base = smem_raw + sizeof(float) * (size_t)IREC_T2_LEN;            // scratch of the serial warps
     auto ctx_base = [&](int c) { return ser_base + tm_serial_bytes<BMAX>(DPm) + (size_t)c * tm_ctx_bytes(DPm, a.NC); };
     auto ctx_scores = [&](int c) { return reinterpret_cast<float*>(ctx_base(c)); };      // [NC]
-    auto ctx_M = [&](int c) { return ctx_scores(c) + a.NC; };                            // [DPm] auxiliary-target means, CI layout
+    auto ctx_M = [&](int c) { return ctx_scores(c) + a.NC; };                            // [DPm] NEGATED auxiliary-target means (-M), CI layout
     auto ctx_next = [&](int c) { return ctx_M(c) + DPm; };                               // [4][DPm] coefficients of the NEXT variable
     auto ctx_hsum = [&](int c) { return reinterpret_cast<int32_t*>(ctx_next(c) + 4 * DPm); };   // [2][32]
     auto ctx_cb = [&](int c) { return reinterpret_cast<uint32_t*>(ctx_hsum(c) + 64); };  // [32] 4 * dlog(h_b)
@@ -539,7 +560,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                     const int arr = pr >> 3, iq = pr & 7;
                     tm_st4(tm_coef + 32 * arr + 4 * iq, next4[arr * (DPm >> 2) + iq * g.P + lg]);
                 }
-                for (int i = tid; i < g.DP; i += nt) s_M[i] = s_next[3 * DPm + i];
+                for (int i = tid; i < g.DP; i += nt) s_M[i] = -s_next[3 * DPm + i];       // the scoring loop adds -M
                 if (tid < 32) s_cb[tid] = tid < Knew ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs_new[tid]) - 1)) : 0u;
                 tm_wait_st();
                 // every serial warp has read NEXT: the context's next compute_next may overwrite it (it follows at once when the
@@ -708,6 +729,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                 const int pos = s_misc[0];
                 if (pos >= a.nb) {
                     retired[c] = true;
+                    if (a.prof && tid == 0) {           // when this context ran out of work (ns, global timer)
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        a.prof[8 * 2 * 1024 + slot] = (long long)now;
+                    }
                     if (tid == 0) s_ctl2[c].finished = 1;
                     tm_fence_before();
                     tm_bar_arrive(TM_BAR_STATE0 + c);     // the scoring warps learn that this context is finished
@@ -831,8 +857,8 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
     const char* pe = getenv("IREC_TM_PROFILE");
     const bool prof_on = pe && pe[0] == '1';
     if (prof_on) {
-        if (!d_prof) cudaMalloc(&d_prof, sizeof(long long) * 8 * 2 * 1024);
-        cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * 2 * 1024, s);
+        if (!d_prof) cudaMalloc(&d_prof, sizeof(long long) * 9 * 2 * 1024);
+        cudaMemsetAsync(d_prof, 0, sizeof(long long) * 9 * 2 * 1024, s);
         a.prof = d_prof;
     }
     switch (p.bmax) {
@@ -846,6 +872,12 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
         std::vector<long long> h(8 * 2 * p.grid);
         cudaStreamSynchronize(s);
         cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        std::vector<long long> fin(2 * p.grid);
+        cudaMemcpy(fin.data(), d_prof + 8 * 2 * 1024, sizeof(long long) * fin.size(), cudaMemcpyDeviceToHost);
+        std::sort(fin.begin(), fin.end());
+        if (!fin.empty())
+            fprintf(stderr, "[tmem profile] contexts retire (ms before the last one): median %.2f, 10%% %.2f, first %.2f\n",
+                    (fin.back() - fin[fin.size() / 2]) * 1e-6, (fin.back() - fin[fin.size() / 10]) * 1e-6, (fin.back() - fin[0]) * 1e-6);
         double tot[8] = { 0 };
         for (int i = 0; i < 2 * p.grid; ++i)
             for (int k = 0; k < 8; ++k) tot[k] += (double)h[(size_t)i * 8 + k];
