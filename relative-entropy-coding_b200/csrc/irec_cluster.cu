@@ -95,7 +95,7 @@ __device__ __forceinline__ void rc_score_round(const char* T2b, const uint16_t* 
 #pragma unroll
         for (int b = 0; b < BSL; ++b) acc[k][b] = 0.f;
     }
-    r2_score_chunk<BSL, NS, TAB>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, tab_t, row, acc);
+    r2_score_chunk<BSL, NS, TAB, false, true>(T2b, dl4, cb4, sa4, A4, E4, M4, beams4, g.DP >> 2, g.P, lg, st, jb, tab_t, row, acc);
     float v[NS * BSL];
 #pragma unroll
     for (int k = 0; k < NS; ++k)

@@ -155,6 +155,17 @@ __device__ __forceinline__ float tf_normal_elem(const TfStream& st, uint64_t j)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic of sm_100 (SASS FMUL2 / FADD2 / FFMA2): one warp-instruction, two IEEE round-to-nearest float32
+// operations on an aligned register pair -- the same bits as two scalar instructions, half the issue slots.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// ---------------------------------------------------------------------------------------------
 // canonical reduction: leaves are 32-dim chunk sums; combine = balanced pairwise tree over the
 // chunk index (pad with zeros to a power of two).  Helpers for the index mapping used in shared
 // memory: dim d = 32*l + i is stored at   ((i>>2)*32 + l)*4 + (i&3)

@@ -61,7 +61,7 @@ struct R2Group {   // beams per inner batch: G * 4 independent gathers in flight
 //   j_base[k] = s_k * D + first dim of the chunk;  q0 = float4 index of the chunk's first quad
 //   row[k]: sample s_k's row of the precomputed exponent table (4 x uint16 per quad, CI layout) or nullptr
 //           (then the exponents come from Philox + dl4 in place)
-template <int BMAX, int NS, bool TAB, bool SPREAD = false>   // SPREAD: in-place two-choice bank assignment (TAB == false only)
+template <int BMAX, int NS, bool TAB, bool SPREAD = false, bool PACK = false>   // SPREAD: in-place two-choice bank assignment (TAB == false only); PACK: FP32x2 arithmetic
 __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, const uint16_t* __restrict__ dl4,
                                                const uint32_t* __restrict__ cb4,
                                                const float4* __restrict__ sa4, const float4* __restrict__ A4,
@@ -104,6 +104,14 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
         }
         const int qi = q0 + iq * P;
         const float4 sa = sa4[qi], A = A4[qi], E = E4[qi], M = M4[qi];
+        // PACK: dims (0,1) and (2,3) of the quad as packed FP32x2 pairs (FMUL2 / FADD2 / FFMA2, irec_common.cuh): v = T*sa,
+        // x = beam + v, d = x - M, t = fma(A, d, E) are four packed instructions per pair -- the same roundings as the scalar
+        // sequence; the accumulation a = fma(t, d, a) stays scalar and sequential in d (the canonical order).  Used where it
+        // measured faster (cluster kernel: 12.8 -> 11.5 ms for configs[2]); the general path got slower with it (166 registers)
+        const f32x2_t sa2[2] = { f2_pack(sa.x, sa.y), f2_pack(sa.z, sa.w) };
+        const f32x2_t A2[2] = { f2_pack(A.x, A.y), f2_pack(A.z, A.w) };
+        const f32x2_t E2[2] = { f2_pack(E.x, E.y), f2_pack(E.z, E.w) };
+        const f32x2_t nM2[2] = { f2_pack(-M.x, -M.y), f2_pack(-M.z, -M.w) };
 #pragma unroll
         for (int b0 = 0; b0 < BMAX; b0 += G) {
             float4 bm[G];
@@ -124,15 +132,31 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
                 }
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    float x, d, t, a = acc[k][b0 + g];
-                    x = __fadd_rn(bm[g].x, __fmul_rn(tv[g][0], sa.x));
-                    d = __fadd_rn(x, -M.x); t = __fmaf_rn(A.x, d, E.x); a = __fmaf_rn(t, d, a);
-                    x = __fadd_rn(bm[g].y, __fmul_rn(tv[g][1], sa.y));
-                    d = __fadd_rn(x, -M.y); t = __fmaf_rn(A.y, d, E.y); a = __fmaf_rn(t, d, a);
-                    x = __fadd_rn(bm[g].z, __fmul_rn(tv[g][2], sa.z));
-                    d = __fadd_rn(x, -M.z); t = __fmaf_rn(A.z, d, E.z); a = __fmaf_rn(t, d, a);
-                    x = __fadd_rn(bm[g].w, __fmul_rn(tv[g][3], sa.w));
-                    d = __fadd_rn(x, -M.w); t = __fmaf_rn(A.w, d, E.w); a = __fmaf_rn(t, d, a);
+                    float a = acc[k][b0 + g];
+                    if (PACK) {
+                        const f32x2_t bm2[2] = { f2_pack(bm[g].x, bm[g].y), f2_pack(bm[g].z, bm[g].w) };
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const f32x2_t x = f2_add(bm2[h2], f2_mul(f2_pack(tv[g][2 * h2], tv[g][2 * h2 + 1]), sa2[h2]));
+                            const f32x2_t d = f2_add(x, nM2[h2]);
+                            const f32x2_t t = f2_fma(A2[h2], d, E2[h2]);
+                            float d0, d1, t0, t1;
+                            f2_unpack(d, d0, d1);
+                            f2_unpack(t, t0, t1);
+                            a = __fmaf_rn(t0, d0, a);
+                            a = __fmaf_rn(t1, d1, a);
+                        }
+                    } else {
+                        float x, d, t;
+                        x = __fadd_rn(bm[g].x, __fmul_rn(tv[g][0], sa.x));
+                        d = __fadd_rn(x, -M.x); t = __fmaf_rn(A.x, d, E.x); a = __fmaf_rn(t, d, a);
+                        x = __fadd_rn(bm[g].y, __fmul_rn(tv[g][1], sa.y));
+                        d = __fadd_rn(x, -M.y); t = __fmaf_rn(A.y, d, E.y); a = __fmaf_rn(t, d, a);
+                        x = __fadd_rn(bm[g].z, __fmul_rn(tv[g][2], sa.z));
+                        d = __fadd_rn(x, -M.z); t = __fmaf_rn(A.z, d, E.z); a = __fmaf_rn(t, d, a);
+                        x = __fadd_rn(bm[g].w, __fmul_rn(tv[g][3], sa.w));
+                        d = __fadd_rn(x, -M.w); t = __fmaf_rn(A.w, d, E.w); a = __fmaf_rn(t, d, a);
+                    }
                     acc[k][b0 + g] = a;
                 }
             }

@@ -102,17 +102,6 @@ __device__ __forceinline__ void tm_tie16(float (&r)[16])
 }
 
 // ---------------------------------------------------------------------------------------------
-// Packed FP32x2 arithmetic of sm_100 (SASS FMUL2 / FADD2 / FFMA2): one warp-instruction, two IEEE round-to-nearest float32
-// operations on an aligned register pair -- the same bits as two scalar instructions, half the issue slots.
-// ---------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
-// ---------------------------------------------------------------------------------------------
 // Chunk sums of NS candidate samples against the HB beams of this warp's half.  Same float32 operation order per
 // candidate-dim as r2_score_chunk / the oracle (beam_score):  x = beam + T2[a + c_b] * sigma_aux;  d = x - M;
 // acc = fma(fma(A, d, E), d, acc).   tm_beams / tm_coef: TMEM addresses (quarter lane base + first column).

@@ -48,7 +48,7 @@ def test_quantile_gathers_stay_software_pipelined(built):
     # unrolled loop bodies = long runs of instructions attributed to the scoring chunk (source lines of r2_score_chunk);
     # the kernel holds several instances (table / in-place exponents, 1 / 10 beams per pass): the hot one is the
     # table-driven pass of 10 beams x 3 samples = the run with >= 100 gathers whose neighbourhood loads 8-byte exponent-table entries (and has no MATCH of the in-place bank assignment)
-    lo, hi = gather_line - 50, gather_line + 20
+    lo, hi = gather_line - 60, gather_line + 45
     runs, i = [], 0
     while i < len(ins):
         if lo <= ins[i][0] <= hi:
