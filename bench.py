@@ -24,6 +24,7 @@ sequential level launches (a level's prior depends on the previous level's sampl
 workload and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -171,6 +172,14 @@ def cpu_numpy_port_sample(n_blocks, threads):
 def cpu_sample_blocks(cores):
     """bounded CPU sample: ~0.4 s of single-core work per coder-block -> 10-20 s per step on all cores"""
     return int(min(1024, max(32 * cores, 64)))
+
+
+def auto_streams(n_img, sm_count=148):
+    """sub-batches per rank: a launch of fewer than ~8 coder-blocks per block context (two contexts per SM) is split in two,
+    so that the CTAs of the next launch take over the SMs the current one's tail leaves idle.  Measured on one B200
+    (profiles/r2_streams_sweep.json): 128 images per rank (1152 blocks, 3.9 per context) 2.69e9 -> 3.04e9 candidates/s
+    with 2 streams (3: 3.00e9, 4: 2.97e9); 256 and 1024 images per rank: no difference (3.05e9 either way)."""
+    return 2 if 9 * n_img <= 8 * 2 * sm_count else 1
 
 
 def workload_name():
@@ -427,6 +436,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--images-total", type=int, default=IMAGES_TOTAL, help="configs[3] is 1024; smaller values are for kernel-tuning runs")
+    ap.add_argument("--streams", type=int, default=0, help="sub-batches per rank, each on its own stream (0 = by launch size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel-tuning runs: skip the end-to-end leg")
     ap.add_argument("--no-c5", action="store_true")
@@ -485,32 +495,56 @@ def main():
     offsets, nb, max_dim = E.make_block_offsets(LATENT, BLOCK, dev, n_items=n_img)
     dims = (offsets[1:] - offsets[:-1]).cpu().numpy()
     lib = N.lib()
-    ws_bytes = int(lib.irec_beam_encode_workspace_bytes(nb, max_dim, S, NBEAMS, MAX_AUX))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     out_idx = [torch.empty((nb, MAX_AUX), dtype=torch.int32, device=dev) for _ in range(LEVELS)]
     out_na = [torch.empty(nb, dtype=torch.int32, device=dev) for _ in range(LEVELS)]
     out_st = [torch.empty(nb, dtype=torch.int32, device=dev) for _ in range(LEVELS)]
     out_sample = [torch.empty(n_img * LATENT, dtype=torch.float32, device=dev) for _ in range(LEVELS)]
-    stream = N.stream_ptr()
     path = int(lib.irec_beam_encode_path(nb, max_dim, S, NBEAMS))
     kernel_name = {2: "k_beam_encode_resident2<20>", 3: "k_beam_encode_tmem<20>", 1: "k_beam_encode_resident<20>"}.get(path, f"path {path}")
 
-    def launch_level(lvl):
-        tl, ts, pl, ps = (t.reshape(-1) for t in devt[lvl])
-        N.check(lib.irec_beam_encode(N.ptr(tl), N.ptr(ts), N.ptr(pl), N.ptr(ps), N.ptr(gather), N.ptr(offsets), nb,
-                                     max_dim, OMEGA, S, NBEAMS, SEED, N.ptr(out_idx[lvl]), MAX_AUX, N.ptr(out_na[lvl]),
-                                     N.ptr(out_st[lvl]), N.ptr(out_sample[lvl]), N.ptr(ws), ws_bytes, stream),
+    # The images of a rank are coded as `n_sub` independent sub-batches, each on its own CUDA stream: the levels of a
+    # sub-batch stay sequential (a level's prior needs the previous level's sample), but sub-batch k's level l + 1 does not
+    # wait for sub-batch j's level l.  A launch is a persistent grid of one CTA per SM whose CTAs retire when the block queue
+    # is empty, so the next stream's CTAs take over the SMs one by one: the tail of one launch (a rank's 1152 coder-blocks
+    # are 3.9 per block context at N = 8) is filled by the head of the next.
+    n_sub = max(1, min(args.streams if args.streams > 0 else auto_streams(n_img), n_img))
+    blocks_per_image = nb // n_img
+    subs = []
+    for k in range(n_sub):
+        lo, hi = unit_range(n_img, k, n_sub)
+        offs_k, nb_k, max_dim_k = E.make_block_offsets(LATENT, BLOCK, dev, n_items=hi - lo)
+        ws_k = torch.empty(int(lib.irec_beam_encode_workspace_bytes(nb_k, max_dim_k, S, NBEAMS, MAX_AUX)), dtype=torch.uint8, device=dev)
+        subs.append({"lo": lo, "hi": hi, "nb": nb_k, "max_dim": max_dim_k, "offsets": offs_k, "ws": ws_k,
+                     "gather": gather[:(hi - lo) * LATENT], "b0": lo * blocks_per_image,
+                     "stream": torch.cuda.Stream(device=dev) if n_sub > 1 else None})
+
+    def launch_level(lvl, sub):
+        lo, hi, b0, nbk = sub["lo"], sub["hi"], sub["b0"], sub["nb"]
+        tl, ts, pl, ps = (t[lo:hi].reshape(-1) for t in devt[lvl])
+        stream = sub["stream"].cuda_stream if sub["stream"] is not None else N.stream_ptr()
+        N.check(lib.irec_beam_encode(N.ptr(tl), N.ptr(ts), N.ptr(pl), N.ptr(ps), N.ptr(sub["gather"]), N.ptr(sub["offsets"]), nbk,
+                                     sub["max_dim"], OMEGA, S, NBEAMS, SEED, N.ptr(out_idx[lvl][b0:b0 + nbk]), MAX_AUX,
+                                     N.ptr(out_na[lvl][b0:b0 + nbk]), N.ptr(out_st[lvl][b0:b0 + nbk]),
+                                     N.ptr(out_sample[lvl][lo * LATENT:hi * LATENT]), N.ptr(sub["ws"]), sub["ws"].numel(), stream),
                 "irec_beam_encode")
 
-    def step_resident(events=None):
+    def step_resident():
+        if n_sub == 1:
+            for lvl in range(LEVELS):
+                launch_level(lvl, subs[0])
+            return
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for sub in subs:
+            sub["stream"].wait_event(fork)
         for lvl in range(LEVELS):
-            if events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            launch_level(lvl)
-            if events is not None:
-                e1.record()
-                events.append((e0, e1))
+            for sub in subs:
+                launch_level(lvl, sub)
+        for sub in subs:
+            join = torch.cuda.Event()
+            join.record(sub["stream"])
+            cur.wait_event(join)
 
     # ---------------- device-resident throughput ----------------
     for _ in range(args.warmup):
@@ -520,11 +554,10 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = N.launch_count()
-    kernel_events = []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
-        step_resident(kernel_events)
+        step_resident()
     stop.record()
     barrier()
     launches = N.launch_count() - launches0
@@ -543,8 +576,9 @@ def main():
         per_level = [work_model(na_all[lvl], dims) for lvl in range(LEVELS)]
         json.dump({"images_per_gpu": n_img, "levels": [{"candidates": c, "candidate_dims": d_, "partitions": p_} for c, d_, p_, _ in per_level]},
                   open(os.environ["IREC_BENCH_DUMP"], "w"))
-    kernel_ms = np.array([a.elapsed_time(b) for a, b in kernel_events]).reshape(args.steps, LEVELS)
-    kernel_ms_avg = float(kernel_ms.mean())
+    # The timed region holds nothing but the level launches, back to back (and overlapping where n_sub > 1): the dominant
+    # kernel's time per LEVEL (all sub-batch launches of a level) is the CUDA-event time of the region / (steps x levels).
+    kernel_ms_avg = ms_total / (args.steps * LEVELS)
     achieved_instr = float(np.mean(per_level_instr)) / (kernel_ms_avg * 1e-3)
 
     # ---------------- end-to-end through the public API (host buffers) ----------------
@@ -552,16 +586,23 @@ def main():
 
     def step_e2e():
         """all levels through the public API from pinned host buffers; the index lists of level l are read back and built
-        while level l + 1 runs (encode_batch(lazy=True)); every level's inputs cross H2D and its sample and indices D2H"""
-        total, pending = 0, None
+        while level l + 1 runs (encode_batch(lazy=True)); every level's inputs cross H2D and its sample and indices D2H.
+        With n_sub > 1 every sub-batch runs this pipeline on its own stream (torch.cuda.stream), as in step_resident."""
+        total, pending = 0, []
         for lvl in range(LEVELS):
-            tl, ts, pl, ps = (t.to(dev, non_blocking=True) for t in host[lvl])
-            get_indices, sample = coder.encode_batch(Normal(tl, ts), Normal(pl, ps), seed=SEED, lazy=True)
-            sample_host[lvl].copy_(sample, non_blocking=True)
-            if pending is not None:
-                total += sum(len(b) for img in pending() for b in img)
-            pending = get_indices
-        total += sum(len(b) for img in pending() for b in img)
+            now = []
+            for sub in subs:
+                lo, hi = sub["lo"], sub["hi"]
+                with torch.cuda.stream(sub["stream"]) if sub["stream"] is not None else contextlib.nullcontext():
+                    tl, ts, pl, ps = (t[lo:hi].to(dev, non_blocking=True) for t in host[lvl])
+                    get_indices, sample = coder.encode_batch(Normal(tl, ts), Normal(pl, ps), seed=SEED, lazy=True)
+                    sample_host[lvl][lo:hi].copy_(sample, non_blocking=True)
+                now.append(get_indices)
+            for get in pending:
+                total += sum(len(b) for img in get() for b in img)
+            pending = now
+        for get in pending:
+            total += sum(len(b) for img in get() for b in img)
         torch.cuda.synchronize()
         return total, sample_host[-1]
 
@@ -635,7 +676,8 @@ def main():
                          "peak": peak_instr / 1e9, "unit": "G lane-instr/s", "frac": achieved_instr / peak_instr,
                          "peak_source": f"{sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
                          "work_model": "W = 10 + 24/B' lane-instr per candidate-dim (SURVEY.md 8d)",
-                         "avg_launch_ms": kernel_ms_avg, "blocks_per_launch": int(nb), "traffic": traffic, "traffic_source": traffic_src,
+                         "avg_launch_ms": kernel_ms_avg, "avg_launch_ms_is": "time of the timed region / (steps x levels): all launches of one level",
+                         "blocks_per_launch": int(nb) // n_sub, "launches_per_level": n_sub, "traffic": traffic, "traffic_source": traffic_src,
                          "smem": {"wavefronts_per_candidate_dim": wf_per_cd, "achieved_gwf_s": smem_rate / 1e9,
                                   "peak_gwf_s": sm_count * sm_max_mhz * 1e6 / 1e9,
                                   "frac": smem_rate / (sm_count * sm_max_mhz * 1e6), "source": traffic_src},

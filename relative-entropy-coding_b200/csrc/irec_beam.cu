@@ -1243,24 +1243,43 @@ static size_t r2_ws_sched_bytes()
     return sizeof(float) * 2 * 4 * 1024 * (size_t)irec_device().sm_count;      // [grid][(2 contexts)][4][DPmax <= 1024]
 }
 // ---- library-owned exponent table, reused across launches (R2TabKey) ----
+// One table per device, shared by every stream.  Cross-stream protocol (host side under the cache mutex, which is HELD from
+// r2_tab_acquire to r2_tab_release, i.e. while one launch is being enqueued):
+//   * rows are append-only while the key (block sizes) stands, so launches of different streams may read the table
+//     concurrently and may append concurrently (same values);
+//   * `ev_w` is recorded after the table-building kernels of every launch; a launch on another stream waits for the latest
+//     one (it precedes that stream's long main kernel, so this does not serialise the main kernels);
+//   * `rd[]` holds one event per recently used stream, recorded after the main kernel.  The table is REWRITTEN (host-known
+//     parameters changed: the stream first waits for every other reader; block sizes changed: decided on the device, allowed
+//     only if all other readers are known to have finished -- otherwise that launch builds a private table in its own
+//     workspace, R2_TAB_PRIVATE) only when nobody else can be reading it.
 #define R2_CACHE_MAX_BYTES ((size_t)256 << 20)
+#define R2_MAX_READERS 8
 struct R2TabCache {
     std::mutex mu;
     void* buf = nullptr; size_t bytes = 0;
     R2TabKey* key = nullptr;                       // device
     int64_t seed = 0; int S = 0, row_stride = 0, cap_aux = 0;
     bool have_params = false;
-    cudaEvent_t ev = nullptr; cudaStream_t last = nullptr; bool ev_valid = false;
+    cudaEvent_t ev_w = nullptr; cudaStream_t last_w = nullptr; bool ev_w_valid = false;
+    struct Reader { cudaStream_t s = nullptr; cudaEvent_t ev = nullptr; bool valid = false; } rd[R2_MAX_READERS];
 };
 static R2TabCache g_tab_cache[64];
 
-struct R2TabUse { uint2* tab; int tab_aux; R2TabKey* key; R2TabCache* cache; };
+struct R2TabUse { uint2* tab; int tab_aux; R2TabKey* key; R2TabCache* cache; uint2* priv; int allow_rekey; };
+
+static bool r2_event_done(cudaEvent_t ev)
+{
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaSuccess) cudaGetLastError();      // cudaErrorNotReady is not an error of ours
+    return e == cudaSuccess;
+}
 
 // table for this launch: the per-device cache when it can be used (capacity, not capturing, IREC_R2_NO_CACHE unset),
 // otherwise `ws_tab` inside the caller's workspace.  On success with a cache the mutex is HELD until r2_tab_release.
 static R2TabUse r2_tab_acquire(uint2* ws_tab, int64_t seed, int S, int max_aux, int row_stride, cudaStream_t s)
 {
-    R2TabUse u{ ws_tab, max_aux, nullptr, nullptr };
+    R2TabUse u{ ws_tab, max_aux, nullptr, nullptr, nullptr, 0 };
     const char* e = getenv("IREC_R2_NO_CACHE");
     if (e && e[0] == '1') return u;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1274,43 +1293,61 @@ static R2TabUse r2_tab_acquire(uint2* ws_tab, int64_t seed, int S, int max_aux, 
     c.mu.lock();
     bool fresh = false;
     if (!c.key) {
-        if (cudaMalloc(&c.key, sizeof(R2TabKey)) != cudaSuccess || cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError(); c.key = nullptr; c.mu.unlock(); return u;
-        }
+        bool ok = cudaMalloc(&c.key, sizeof(R2TabKey)) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&c.ev_w, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < R2_MAX_READERS; ++i)
+            ok = cudaEventCreateWithFlags(&c.rd[i].ev, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); c.key = nullptr; c.mu.unlock(); return u; }
         fresh = true;
     }
     if (need > c.bytes) {
         if (c.buf) { cudaDeviceSynchronize(); cudaFree(c.buf); c.buf = nullptr; c.bytes = 0; }
-        if (cudaMalloc(&c.buf, need) != cudaSuccess) { cudaGetLastError(); c.mu.unlock(); return u; }
+        if (cudaMalloc(&c.buf, need) != cudaSuccess) { cudaGetLastError(); c.have_params = false; c.mu.unlock(); return u; }
         c.bytes = need;
         fresh = true;
     }
-    if (c.ev_valid && c.last != s) cudaStreamWaitEvent(s, c.ev, 0);          // another stream may still be using the table
     const bool same = c.have_params && c.seed == seed && c.S == S && c.row_stride == row_stride && c.cap_aux >= cap_aux;
+    int allow_rekey = 1;
     if (fresh || !same) {
+        // host-known parameters changed: the table is rebuilt, so this stream queues behind every other reader
+        for (auto& r : c.rd)
+            if (r.valid && r.s != s && !r2_event_done(r.ev)) cudaStreamWaitEvent(s, r.ev, 0);
+        if (c.ev_w_valid && c.last_w != s) cudaStreamWaitEvent(s, c.ev_w, 0);
         cudaMemsetAsync(c.key, 0, sizeof(R2TabKey), s);
         c.seed = seed; c.S = S; c.row_stride = row_stride; c.cap_aux = cap_aux; c.have_params = true;
+    } else {
+        if (c.ev_w_valid && c.last_w != s) cudaStreamWaitEvent(s, c.ev_w, 0);      // the table as the latest builder left it
+        for (auto& r : c.rd)
+            if (r.valid && r.s != s && !r2_event_done(r.ev)) allow_rekey = 0;      // somebody else may be reading
     }
     u.tab = reinterpret_cast<uint2*>(c.buf); u.tab_aux = c.cap_aux; u.key = c.key; u.cache = &c;
+    u.priv = ws_tab; u.allow_rekey = allow_rekey;
     return u;
 }
 static void r2_tab_release(const R2TabUse& u, cudaStream_t s)
 {
     if (!u.cache) return;
-    cudaEventRecord(u.cache->ev, s);
-    u.cache->ev_valid = true; u.cache->last = s;
-    u.cache->mu.unlock();
+    R2TabCache& c = *u.cache;
+    R2TabCache::Reader* slot = nullptr;
+    for (auto& r : c.rd) if (r.valid && r.s == s) { slot = &r; break; }
+    if (!slot) for (auto& r : c.rd) if (!r.valid || r2_event_done(r.ev)) { slot = &r; break; }
+    if (!slot) { slot = &c.rd[0]; cudaEventSynchronize(slot->ev); }          // more than R2_MAX_READERS streams in flight
+    cudaEventRecord(slot->ev, s);
+    slot->s = s; slot->valid = true;
+    c.mu.unlock();
 }
 // exponent rows of this launch (skipping what the cache already holds) + the cache bookkeeping kernel
-static void r2_build_table(const R2TabUse& u, const R2Plan* dplan, int64_t seed, int S, int max_aux, int row_stride, cudaStream_t s)
+static void r2_build_table(const R2TabUse& u, R2Plan* dplan, int64_t seed, int S, int max_aux, int row_stride, cudaStream_t s)
 {
     const int64_t items = (int64_t)R2_MAX_SIZES * max_aux * S * 8;          // one thread per gather family
     const int grid = (int)std::min<int64_t>((items + 127) / 128, (int64_t)irec_device().sm_count * 32);
-    k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, u.tab_aux, row_stride, u.tab, u.key);
+    k_r2_exps<<<grid, 128, 0, s>>>(dplan, irec_device().d_dl4, seed, S, max_aux, u.tab_aux, row_stride, u.tab, u.key, u.priv, u.allow_rekey);
     irec_count_launch();
     if (u.key) {
-        k_r2_key_commit<<<1, 1, 0, s>>>(dplan, u.key, max_aux);
+        k_r2_key_commit<<<1, 1, 0, s>>>(dplan, u.key, max_aux, u.allow_rekey);
         irec_count_launch();
+        cudaEventRecord(u.cache->ev_w, s);
+        u.cache->ev_w_valid = true; u.cache->last_w = s;
     }
 }
 
@@ -1934,13 +1971,13 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             r2_build_table(u, dplan, seed, S, max_aux, row_stride, s);
             const int rc = irec_launch_cluster(cluster_G, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim,
                                                omega, S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
-                                               dplan, u.tab, u.tab_aux, s);
+                                               dplan, u.tab, u.tab_aux, u.priv, s);
             r2_tab_release(u, s);
             return rc;
         }
         return irec_launch_cluster(cluster_G, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim, omega,
                                    S, B, seed, out_indices, max_aux, out_n_aux, out_status, out_sample, hist, order,
-                                   nullptr, tab, max_aux, s);
+                                   nullptr, tab, max_aux, nullptr, s);
     }
     if (!irec_force_general() && (rchoice == 0 || rchoice == 3)) {
         TmemPlan tp;
@@ -1963,12 +2000,12 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
                 r2_build_table(u, dplan, seed, S, max_aux, tp.DPmax >> 2, s);
                 const int rc = irec_launch_tmem(tp, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, S, B, seed,
                                                 out_indices, max_aux, out_n_aux, out_status, out_sample, hist, sched, counter, order,
-                                                dplan, u.tab, u.tab_aux, s);
+                                                dplan, u.tab, u.tab_aux, u.priv, s);
                 r2_tab_release(u, s);
                 return rc;
             }
             return irec_launch_tmem(tp, t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, omega, S, B, seed, out_indices,
-                                    max_aux, out_n_aux, out_status, out_sample, hist, sched, counter, order, nullptr, nullptr, max_aux, s);
+                                    max_aux, out_n_aux, out_status, out_sample, hist, sched, counter, order, nullptr, nullptr, max_aux, nullptr, s);
         }
         if (rchoice == 3) return irec_fail(IREC_E_CAPACITY, "beam_encode: IREC_RESIDENT=3 but the sizes do not fit the tensor-memory kernel");
     }
@@ -1987,7 +2024,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
             a.hist = reinterpret_cast<int2*>(w + 512);
             a.sched = reinterpret_cast<float*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux));
             a.work_counter = counter; a.DPmax = plan2.DPmax; a.NC = plan2.NC;
-            a.plan = nullptr; a.tab = nullptr; a.tab_aux = max_aux;
+            a.plan = nullptr; a.tab = nullptr; a.tab_aux = max_aux; a.tab_priv = nullptr;
             // distinct block sizes + the queue order (largest blocks first)
             R2Plan* dplan = reinterpret_cast<R2Plan*>(w + 256);
             int32_t* order = reinterpret_cast<int32_t*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes());
@@ -2001,7 +2038,7 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
                 uint2* tab = reinterpret_cast<uint2*>(w + r2_ws_hist_bytes(plan2.bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb));
                 const R2TabUse u = r2_tab_acquire(tab, seed, S, max_aux, plan2.DPmax >> 2, s);
                 r2_build_table(u, dplan, seed, S, max_aux, plan2.DPmax >> 2, s);
-                a.plan = dplan; a.tab = u.tab; a.tab_aux = u.tab_aux;
+                a.plan = dplan; a.tab = u.tab; a.tab_aux = u.tab_aux; a.tab_priv = u.priv;
                 launch_resident2(plan2, a, s);
                 r2_tab_release(u, s);
                 return irec_check_launch("k_beam_encode_resident2");

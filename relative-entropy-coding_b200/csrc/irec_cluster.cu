@@ -141,6 +141,7 @@ struct ClusterArgs {
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
     int tab_aux;
+    const uint2* tab_priv; // the launch's own table (workspace), used when plan->use_private
     int G;                 // CTAs per cluster
 };
 
@@ -238,12 +239,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) k_beam_encode_cluster(const Clu
     const int D = (int)(a.offs[blk + 1] - off);
     const BeamGeom g = make_geom(D);
     const int row_stride = DPm >> 2;
-    const uint2* tab_blk = nullptr;
-    if (a.tab) {
-#pragma unroll
-        for (int k = 0; k < R2_MAX_SIZES; ++k)
-            if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
-    }
+    const uint2* tab_blk = r2_tab_of_size(a.plan, a.tab, a.tab_aux, a.tab_priv, a.max_aux, a.S, row_stride, D);
 
     // ---- load + KL (coder.py:499-501), redundantly in every CTA ----
     for (int i = tid; i < g.DP; i += nt) {
@@ -430,7 +426,7 @@ static int launch_cluster_t(const ClusterArgs& a, cudaStream_t s)
 int irec_launch_cluster(int G, const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
                         const int64_t* gidx, const int64_t* offs, int nb, int max_D, float omega, int S, int B, int64_t seed,
                         int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
-                        int2* hist, const int32_t* order, const void* plan, const void* tab, int tab_aux, cudaStream_t s)
+                        int2* hist, const int32_t* order, const void* plan, const void* tab, int tab_aux, const void* tab_priv, cudaStream_t s)
 {
     ClusterArgs a;
     a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
@@ -439,7 +435,7 @@ int irec_launch_cluster(int G, const float* t_loc, const float* t_scale, const f
     a.out_sample = out_sample; a.T2 = irec_device().d_T2; a.dl4 = irec_device().d_dl4;
     a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     a.hist = hist; a.DPmax = make_geom(max_D).DP; a.NC = ((S * B + 31) / 32) * 32;
-    a.order = order; a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux;
+    a.order = order; a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux; a.tab_priv = reinterpret_cast<const uint2*>(tab_priv);
     a.G = G;
     const int bpc = (B + G - 1) / G;
     switch (bpc) {

@@ -37,7 +37,8 @@ size_t irec_cluster_hist_bytes(int nb, int max_aux);
 int irec_launch_cluster(int G, const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
                         const int64_t* gidx, const int64_t* offs, int nb, int max_D, float omega, int S, int B, int64_t seed,
                         int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
-                        int2* hist, const int32_t* order, const void* plan, const void* tab, int tab_aux, cudaStream_t s);
+                        int2* hist, const int32_t* order, const void* plan, const void* tab, int tab_aux, const void* tab_priv,
+                        cudaStream_t s);
 
 // irec_tmem.cu: persistent kernel with the beams in tensor memory, two coder-blocks in flight per SM
 struct TmemPlan { int bmax; int DPmax; int NC; int grid; size_t smem; };
@@ -46,7 +47,7 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
                      const int64_t* gidx, const int64_t* offs, int nb, float omega, int S, int B, int64_t seed,
                      int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
                      int2* hist, float* sched, int* work_counter, const int32_t* order, const void* plan, const void* tab, int tab_aux,
-                     cudaStream_t s);
+                     const void* tab_priv, cudaStream_t s);
 
 #define IREC_ENSURE_INIT()                     \
     do {                                       \

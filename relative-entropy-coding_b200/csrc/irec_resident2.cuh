@@ -319,7 +319,7 @@ __device__ __forceinline__ void r2_score_partition(const char* T2b, const uint16
 struct R2Plan {
     int32_t n_sizes;               // distinct block sizes found (may exceed R2_MAX_SIZES: the rest uses in-place Philox)
     int32_t D[R2_MAX_SIZES];
-    int32_t pad;
+    int32_t use_private;           // set by k_r2_key_commit: this launch's table is the one in its own workspace, not the shared cache
 };
 // Device-side description of what a (library-owned, reused) exponent table currently holds.  The table depends on
 // (seed, S, row stride, the block sizes, t) only -- a model codes all of its latent tensors with the same seed
@@ -331,6 +331,20 @@ struct R2TabKey {
     int32_t filled;                // rows t < filled are present for both sizes
 };
 
+// table base of block size D for the main kernels (nullptr: this size has no table)
+__device__ __forceinline__ const uint2* r2_tab_of_size(const R2Plan* plan, const uint2* tab, int tab_aux, const uint2* tab_priv,
+                                                       int max_aux, int S, int row_stride, int D)
+{
+    if (!tab) return nullptr;
+    const bool priv = tab_priv != nullptr && plan->use_private != 0;
+    const uint2* base = priv ? tab_priv : tab;
+    const int rows = priv ? max_aux : tab_aux;
+    const uint2* r = nullptr;
+#pragma unroll
+    for (int k = 0; k < R2_MAX_SIZES; ++k)
+        if (plan->D[k] == D) r = base + (size_t)k * rows * S * row_stride;
+    return r;
+}
 #ifndef IREC_R2_DEVICE_ONLY      // the __global__ kernels below belong to irec_beam.cu only
 // Also writes `order`: the coder-blocks sorted by decreasing size (counting sort), the sequence in which the
 // persistent CTAs draw them from the queue -- the short blocks of a tensor (its last, partial block) go last and
@@ -377,29 +391,51 @@ __global__ void __launch_bounds__(1024) k_r2_plan(const int64_t* __restrict__ of
 // serves more than `cap` lanes: greedy "less loaded of the two banks", one-hop relocation when both are full,
 // cap raised from 2 only if that fails.  Any assignment yields the same values (T2[a] == T2[a + 10006]).
 #define R2_BANK_SHIFT (IREC_ORD & 31u)
-__global__ void k_r2_key_commit(const R2Plan* __restrict__ plan, R2TabKey* key, int max_aux)
+// What a launch does with the shared (library-owned) table, decided on the device from the key -- identically by
+// k_r2_exps and k_r2_key_commit of the same launch (the key cannot change its block sizes in between: a re-key needs every
+// other stream's launches to have finished, r2_tab_acquire):
+//   R2_TAB_APPEND : the table holds these block sizes; rows >= key->filled are added (rows below are never rewritten, so
+//                   launches of other streams may be reading them)
+//   R2_TAB_REKEY  : other sizes, and the host has established that no other stream can be using the table: rebuilt in place
+//   R2_TAB_PRIVATE: other sizes while another stream may be reading: the launch builds its own table in its workspace
+enum { R2_TAB_APPEND = 0, R2_TAB_REKEY = 1, R2_TAB_PRIVATE = 2 };
+__device__ __forceinline__ int r2_tab_mode(const R2Plan* plan, const R2TabKey* key, int allow_rekey)
 {
     bool same = key->valid != 0;
+#pragma unroll
     for (int k = 0; k < R2_MAX_SIZES; ++k) same = same && key->D[k] == plan->D[k];
-    const int have = same ? key->filled : 0;
-    for (int k = 0; k < R2_MAX_SIZES; ++k) key->D[k] = plan->D[k];
-    key->filled = have > max_aux ? have : max_aux;
-    key->valid = 1;
+    return same ? R2_TAB_APPEND : (allow_rekey ? R2_TAB_REKEY : R2_TAB_PRIVATE);
+}
+__global__ void k_r2_key_commit(R2Plan* __restrict__ plan, R2TabKey* key, int max_aux, int allow_rekey)
+{
+    const int mode = r2_tab_mode(plan, key, allow_rekey);
+    if (mode == R2_TAB_APPEND) {
+        atomicMax(&key->filled, max_aux);
+    } else if (mode == R2_TAB_REKEY) {
+        for (int k = 0; k < R2_MAX_SIZES; ++k) key->D[k] = plan->D[k];
+        key->filled = max_aux;
+        key->valid = 1;
+    } else {
+        plan->use_private = 1;
+    }
 }
 
 // tab_aux: rows per size the table is laid out for (>= max_aux); key: nullptr, or the cache key -- rows it already
 // covers for these block sizes are skipped (k_r2_key_commit, launched right after, records the new state)
 __global__ void __launch_bounds__(128) k_r2_exps(const R2Plan* __restrict__ plan, const uint16_t* __restrict__ dl4,
                                                  int64_t seed, int S, int max_aux, int tab_aux, int row_stride,
-                                                 uint2* __restrict__ tab, const R2TabKey* __restrict__ key)
+                                                 uint2* __restrict__ tab, const R2TabKey* __restrict__ key,
+                                                 uint2* __restrict__ tab_priv, int allow_rekey)
 {
     int t_first = 0;
     if (key) {
-        bool same = key->valid != 0;
-#pragma unroll
-        for (int k = 0; k < R2_MAX_SIZES; ++k) same = same && key->D[k] == plan->D[k];
-        t_first = same ? key->filled : 0;
-        if (t_first >= max_aux) return;
+        const int mode = r2_tab_mode(plan, key, allow_rekey);
+        if (mode == R2_TAB_APPEND) {
+            t_first = key->filled;                 // may grow under us (another stream appending): rows are then written twice, same values
+            if (t_first >= max_aux) return;
+        } else if (mode == R2_TAB_PRIVATE) {
+            tab = tab_priv; tab_aux = max_aux;     // layout of the workspace table: [R2_MAX_SIZES][max_aux][S][row_stride]
+        }
     }
     const int64_t per_size = (int64_t)max_aux * S * 8;
     const int64_t total = per_size * R2_MAX_SIZES;
@@ -664,6 +700,7 @@ struct Resident2Args {
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
     int tab_aux;           // rows per size in the table layout (>= max_aux)
+    const uint2* tab_priv; // [R2_MAX_SIZES][max_aux][S][DPmax / 4] in the launch's workspace, used when plan->use_private (or nullptr)
 };
 
 template <int BMAX>
@@ -716,12 +753,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_beam_encode_resident2(const R
         const int D = (int)(a.offs[blk + 1] - off);
         const BeamGeom g = make_geom(D);
         const int row_stride = DPm >> 2;
-        const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
-        if (a.tab) {
-#pragma unroll
-            for (int k = 0; k < R2_MAX_SIZES; ++k)
-                if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
-        }
+        // exponent table of this block size (if it has one)
+        const uint2* tab_blk = r2_tab_of_size(a.plan, a.tab, a.tab_aux, a.tab_priv, a.max_aux, a.S, row_stride, D);
 
         // ---- load + KL (coder.py:499-501) ----
         for (int i = tid; i < g.DP; i += nt) {

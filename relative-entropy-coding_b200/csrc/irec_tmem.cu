@@ -280,6 +280,7 @@ struct TmemArgs {
     const R2Plan* plan;    // distinct block sizes with an exponent table (nullptr: no table)
     const uint2* tab;      // [R2_MAX_SIZES][tab_aux][S][DPmax / 4]
     int tab_aux;
+    const uint2* tab_priv; // the launch's own table (workspace), used when plan->use_private
     int score_lock;        // unused (kept for A/B builds)
     long long* prof;       // nullptr, or [2 * gridDim.x][8] cycle counters per context (IREC_TM_PROFILE=1; diagnostics)
 };
@@ -734,12 +735,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_beam_encode_tmem(const TmemAr
                 const int64_t off = a.offs[blk];
                 const int D = (int)(a.offs[blk + 1] - off);
                 const BeamGeom g = make_geom(D);
-                const uint2* tab_blk = nullptr;            // exponent table of this block size (if it has one)
-                if (a.tab) {
-#pragma unroll
-                    for (int k = 0; k < R2_MAX_SIZES; ++k)
-                        if (a.plan->D[k] == D) tab_blk = a.tab + (size_t)k * a.tab_aux * a.S * row_stride;
-                }
+                // exponent table of this block size (if it has one)
+                const uint2* tab_blk = r2_tab_of_size(a.plan, a.tab, a.tab_aux, a.tab_priv, a.max_aux, a.S, row_stride, D);
                 // ---- load (CI layout, zero padding) ----
                 for (int i = tid; i < g.DP; i += nt) {
                     const int l = (i >> 2) & (g.P - 1), iq = i / (4 * g.P), e = i & 3;       // CI(P): i = (iq * P + l) * 4 + e
@@ -823,7 +820,7 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
                      const int64_t* gidx, const int64_t* offs, int nb, float omega, int S, int B, int64_t seed,
                      int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
                      int2* hist, float* sched, int* work_counter, const int32_t* order, const void* plan, const void* tab, int tab_aux,
-                     cudaStream_t s)
+                     const void* tab_priv, cudaStream_t s)
 {
     TmemArgs a;
     a.t_loc = t_loc; a.t_scale = t_scale; a.p_loc = p_loc; a.p_scale = p_scale;
@@ -833,6 +830,7 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
     a.ratio_tab = irec_ratio_tab(); a.ratio_len = irec_ratio_len();
     a.hist = hist; a.work_counter = work_counter; a.DPmax = p.DPmax; a.NC = p.NC; a.sched = sched; a.order = order;
     a.plan = reinterpret_cast<const R2Plan*>(plan); a.tab = reinterpret_cast<const uint2*>(tab); a.tab_aux = tab_aux;
+    a.tab_priv = reinterpret_cast<const uint2*>(tab_priv);
     a.score_lock = 0;
     k_tm_kl_status<<<std::min(nb, 8 * irec_device().sm_count), 256, 0, s>>>(t_loc, t_scale, p_loc, p_scale, gidx, offs, nb, omega, max_aux,
                                                                            a.ratio_len, out_n_aux, out_status);

@@ -504,6 +504,54 @@ def test_exponent_table_cache_is_transparent(cuda):
         assert ai == ri and torch.equal(as_, rs)
 
 
+def test_exponent_table_cache_across_streams(cuda):
+    """The exponent table is shared by all streams of a device (csrc/irec_beam.cu, r2_tab_acquire): launches of different
+    streams read it concurrently and append rows concurrently; a launch with OTHER block sizes may rewrite it only when no
+    other stream can be reading, and otherwise builds a private table in its workspace.  Launches of two streams are
+    enqueued back to back without any host synchronisation -- same sizes (shared reads), more auxiliary variables on one
+    stream (append under a reader), other sizes (private table / re-key) -- and every result must equal IREC_R2_NO_CACHE=1."""
+    import os
+    import torch
+    from irec_b200 import Normal
+    from rec.coding import BeamSearchCoder
+
+    def batch(n_img, n, seed, boost=1.0):
+        arrs = [synth.c2(n, data_seed=seed + i) for i in range(n_img)]
+        tl, ts, pl, ps = (np.stack([a[k] for a in arrs]) for k in range(4))
+        tl = (pl + boost * (tl - pl)).astype(np.float32)
+        return Normal(tl, ts, device=cuda), Normal(pl, ps, device=cuda)
+
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=1000)
+    a1, a2, a3 = batch(80, 3192, 100), batch(80, 3192, 300), batch(80, 3192, 500, boost=1.7)      # 320 coder-blocks each
+    b1, b2 = batch(60, 2500, 700), batch(60, 2700, 900)                                            # other block sizes
+    # (stream, inputs): consecutive entries overlap on the device
+    plan = [(0, a1), (1, a2), (0, a1), (1, a3), (0, a2), (1, b1), (0, a1), (1, b2), (0, b1), (1, a3), (0, b2), (1, b1)]
+
+    def run(streams):
+        pend = []
+        for k, (t, p) in plan:
+            with torch.cuda.stream(streams[k]):
+                pend.append(coder.encode_batch(t, p, seed=42, lazy=True))
+        return [(get(), smp) for get, smp in pend]
+
+    os.environ["IREC_R2_NO_CACHE"] = "1"
+    try:
+        cur = torch.cuda.current_stream()
+        ref = run([cur, cur])
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["IREC_R2_NO_CACHE"]
+    s = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in s:
+        st.wait_stream(torch.cuda.current_stream())
+    for rep in range(2):
+        got = run(s)
+        torch.cuda.synchronize()
+        for i, ((ri, rs), (gi, gs)) in enumerate(zip(ref, got)):
+            assert gi == ri, f"launch {i} of repetition {rep}: indices differ"
+            assert torch.equal(gs, rs), f"launch {i} of repetition {rep}: sample differs"
+
+
 # ------------------------------------------------------------------------------------------ round 2: decode validation, IS candidate table
 def test_decode_rejects_index_lists_beyond_the_ratio_table(cuda):
     """a learned ratio table shorter than an index list must raise CodingError (reference coder.py:226-231),
