@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare with the CPU oracle where S is small enough")
     ap.add_argument("--graph", action="store_true", help="replay the per-variable step loop from a CUDA graph")
+    ap.add_argument("--fused", action="store_true", help="one cooperative launch for all variables (k_gp_fused), as bench.py's c5")
     args = ap.parse_args()
 
     import torch
@@ -61,6 +62,9 @@ def main():
         d = [torch.as_tensor(a, device=dev).contiguous() for a in (mu, sig, pl, ps)]
         blk = engine.ShardedBeamBlock(D, S, B, omega, max_aux=256, device=dev)
         idx, sample = blk.encode(*d, seed=42)            # warm-up + result
+        if args.fused:
+            idx_f, sample_f = blk.encode_fused(*d, seed=42)
+            assert idx_f == idx and torch.equal(sample_f, sample), "fused encode differs from the multi-launch one"
         if args.graph:
             idx_g, sample_g = blk.encode_graphed(*d, seed=42)        # captures; must reproduce the eager result
             assert idx_g == idx and torch.equal(sample_g, sample), "graphed encode differs from the eager one"
@@ -71,6 +75,12 @@ def main():
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            if args.fused:
+                blk.encode_fused(*d, seed=42)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+                continue
             n_aux = blk.init(*d, seed=42)
             if args.graph:
                 blk._graphs[n_aux].replay()
@@ -87,7 +97,7 @@ def main():
         n_aux = len(idx)
         cand = S + (n_aux - 1) * S * min(B, S)
         line = {"workload": "C5 sweep: one coder-block, candidate range sharded", "omega_bits": bits, "S": S, "D": D, "n_beams": B,
-                "n_aux": n_aux, "n_gpus": world, "cuda_graph": bool(args.graph),
+                "n_aux": n_aux, "n_gpus": world, "cuda_graph": bool(args.graph), "fused": bool(args.fused),
                 "exchange": ("peer-memory stores (irec_p2p_exchange)" if blk.p2p is not None else ("nccl all_gather" if world > 1 else "none")), "ms": ms, "candidates_per_sec": cand / (ms * 1e-3),
                 "candidate_dims_per_sec": cand * D / (ms * 1e-3), "partitions_per_sec": n_aux / (ms * 1e-3)}
         if args.check and S * B * D <= 4e8:

@@ -542,6 +542,14 @@ __global__ void __launch_bounds__(256) k_gp_score_topb(const ScoreArgs a)
 #ifndef GP2_THREADS
 #define GP2_THREADS 384
 #endif
+// In-place two-choice bank assignment of the quantile gathers (r2_spread_banks: one match.any per exponent) -- OFF.  It lowers
+// the gathers from 3.5 to 2.7 shared-memory wavefronts, but MATCH.ANY itself is the slower resource: A/B of k_gp_fused<20> on
+// one B200, C5 at S = 2^24: 117.0 ms with, 89.9 ms without (profiles/r2_gp_variants.log; the consumers of the match held 30 %
+// of the warp samples in profiles/r1_gp_score2_ncu.md).  Generating the exponents one quad ahead did not hide it (125 ms).
+#ifndef GP2_SPREAD
+#define GP2_SPREAD false
+#endif
+#define GP_DL4_LEN 10008     // uint16 entries of the discrete-log table copied to shared memory (d_dl4 is allocated with 10008)
 #ifndef GP2_NS
 #define GP2_NS 2            // sample groups per warp and round: a beam quad read from global memory serves 8 candidate-dims
 #endif            // (A/B at S = 2^24, one GPU: 512 threads x 1 group 118 ms, 384 x 2 108 ms, 512 x 2 109 ms, 256 x 3 137 ms)
@@ -593,11 +601,15 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_score_topb2(const Score2A
     int32_t* s_cnt = s_ctl + 4;                                      // [1] candidate count
     float* s_tau = reinterpret_cast<float*>(s_cnt + 1);              // [1]
     uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_tau + 1) + 2;     // [32] 4 * dlog(h_b)
+    uint16_t* s_dl4 = reinterpret_cast<uint16_t*>(s_cb + 32);        // [GP_DL4_LEN] the discrete-log table (r2_exp4<true>)
 
     {
         const float4* src = reinterpret_cast<const float4*>(a.T2);
         float4* dst = reinterpret_cast<float4*>(s_T2);
         for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
+        const uint32_t* dsrc = reinterpret_cast<const uint32_t*>(a.dl4);
+        uint32_t* ddst = reinterpret_cast<uint32_t*>(s_dl4);
+        for (int i = tid; i < GP_DL4_LEN / 2; i += nt) ddst[i] = dsrc[i];
     }
     if (tid == 0) { *s_cnt = 0; *s_tau = __int_as_float(0xff800000); }
     const int32_t* hs = st_hsum(a.state, cur, B, g.DP);
@@ -641,8 +653,8 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_score_topb2(const Score2A
             for (int k = 0; k < GP2_NS; ++k)
 #pragma unroll
                 for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
-            r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2), g.DP >> 2,
-                                                    g.P, lg, st, jb, nullptr, row, acc);
+            r2_score_chunk<HB, GP2_NS, false, GP2_SPREAD, false, true>(T2b, s_dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * (g.DP >> 2),
+                                                                       g.DP >> 2, g.P, lg, st, jb, nullptr, row, acc);
             float v[GP2_NS * HB];
 #pragma unroll
             for (int k = 0; k < GP2_NS; ++k)
@@ -850,11 +862,15 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
     uint32_t* s_cb = reinterpret_cast<uint32_t*>(s_flag + 2);        // [32] 4 * dlog(h_b)
     int32_t* s_hsum = reinterpret_cast<int32_t*>(s_cb + 32);         // [2][32]
     irec_record_t* s_win = reinterpret_cast<irec_record_t*>(s_hsum + 64);   // [32]
+    uint16_t* s_dl4 = reinterpret_cast<uint16_t*>(s_win + 32);       // [GP_DL4_LEN] the discrete-log table (r2_exp4<true>)
 
     {
         const float4* src = reinterpret_cast<const float4*>(a.T2);
         float4* dst = reinterpret_cast<float4*>(s_T2);
         for (int i = tid; i < IREC_T2_LEN / 4; i += nt) dst[i] = src[i];
+        const uint32_t* dsrc = reinterpret_cast<const uint32_t*>(a.dl4);
+        uint32_t* ddst = reinterpret_cast<uint32_t*>(s_dl4);
+        for (int i = tid; i < GP_DL4_LEN / 2; i += nt) ddst[i] = dsrc[i];
     }
     for (int i = tid; i < DP; i += nt) {
         s_cv[i] = st_arr(a.state, 0, DP)[i]; s_tv[i] = st_arr(a.state, 1, DP)[i]; s_dmu[i] = st_arr(a.state, 2, DP)[i];
@@ -920,8 +936,8 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
                     for (int k = 0; k < GP2_NS; ++k)
 #pragma unroll
                         for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
-                    r2_score_chunk<HB, GP2_NS, false, true>(T2b, a.dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
-                                                            g.P, lg, st, jb, nullptr, row, acc);
+                    r2_score_chunk<HB, GP2_NS, false, GP2_SPREAD, false, true>(T2b, s_dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
+                                                                               g.P, lg, st, jb, nullptr, row, acc);
                     float v[GP2_NS * HB];
 #pragma unroll
                     for (int k = 0; k < GP2_NS; ++k)
@@ -1460,7 +1476,7 @@ static int gp_score_grid(int D, int64_t n_samples)
 static size_t gp2_score_smem(int cand_cap)
 {
     return sizeof(float) * ((size_t)IREC_T2_LEN + (size_t)cand_cap + GP2_THREADS + 32) +
-           sizeof(int32_t) * ((size_t)cand_cap + 32 + TOPK_CAP + 4 + 4 + 32) + 16;
+           sizeof(int32_t) * ((size_t)cand_cap + 32 + TOPK_CAP + 4 + 4 + 32) + sizeof(uint16_t) * GP_DL4_LEN + 16;
 }
 static int gp2_cand_cap(int D, int bmax)
 {
@@ -1544,7 +1560,8 @@ static int launch_gp_score(int bmax, const ScoreArgs& a, int grid, size_t smem, 
 static size_t fused_smem(int DP, int bmax, int cap)
 {
     return sizeof(float) * ((size_t)IREC_T2_LEN + 8 * (size_t)DP + 2 * (size_t)bmax * DP + cap + GP2_THREADS + 32 + 1) +
-           sizeof(int32_t) * ((size_t)cap + 32 + TOPK_CAP + 4 + 1 + 2 + 32 + 64) + sizeof(irec_record_t) * 32 + 64;
+           sizeof(int32_t) * ((size_t)cap + 32 + TOPK_CAP + 4 + 1 + 2 + 32 + 64) + sizeof(irec_record_t) * 32 +
+           sizeof(uint16_t) * GP_DL4_LEN + 64;
 }
 template <int BMAX>
 static int launch_fused_t(const FusedArgs& a, int grid, size_t smem, cudaStream_t s)
@@ -1910,6 +1927,7 @@ int irec_beam_encode_fused(void* state, int D, int B, int64_t s_begin, int64_t s
 size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, int B, int max_aux)
 {
     if (irec_init() != IREC_OK) return 0;
+    if (B > 32) return max_block_dim <= 1024 ? irec_wide_workspace_bytes(nb, (int)max_block_dim, S, B, max_aux) : 0;
     const int bmax = B <= 1 ? 1 : (B <= 10 ? 10 : (B <= 20 ? 20 : 32));     // the largest beam capacity any persistent kernel picks for B
     const size_t resident = r2_ws_hist_bytes(bmax, max_aux) + r2_ws_sched_bytes() + r2_ws_order_bytes(nb) +
                             r2_table_bytes((int)max_block_dim, S, max_aux);
@@ -1922,7 +1940,8 @@ size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, in
 int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B)
 {
     IREC_ENSURE_INIT();
-    if (nb <= 0 || S <= 0 || B <= 0 || B > 32 || max_block_dim <= 0) return 0;
+    if (nb <= 0 || S <= 0 || B <= 0 || max_block_dim <= 0) return 0;
+    if (B > 32) return (max_block_dim <= 1024 && irec_wide_supported(nb, (int)max_block_dim, S, B)) ? 4 : 0;
     const int rchoice = resident_choice();
     if (irec_force_general()) return 0;
     if (rchoice == 0) {
@@ -1945,11 +1964,19 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
     cudaStream_t s = (cudaStream_t)stream;
     if (nb <= 0) return IREC_OK;
     if (S <= 0 || B <= 0 || max_aux <= 0 || max_block_dim <= 0) return irec_fail(IREC_E_INVALID, "beam_encode: bad sizes");
-    if (B > 32) return irec_fail(IREC_E_CAPACITY, "beam_encode: n_beams > 32 is not supported");
     if ((int64_t)S * B >= (1LL << 31)) return irec_fail(IREC_E_CAPACITY, "beam_encode: S*B must be < 2^31");
+    if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "beam_encode: kl_per_partition must be > 0");
+    if (B > 32) {
+        // wide beams (irec_wide.cu): the reference has no limit on n_beams (beam_search_coder.py:15-30)
+        if (max_block_dim > 1024 || !irec_wide_supported(nb, (int)max_block_dim, S, B))
+            return irec_fail(IREC_E_CAPACITY, "beam_encode: n_beams > 32 needs n_beams <= 1024, block dims <= 1024 and S * n_beams < 2^31");
+        if (workspace_bytes < irec_wide_workspace_bytes(nb, (int)max_block_dim, S, B, max_aux))
+            return irec_fail(IREC_E_CAPACITY, "beam_encode: workspace too small");
+        return irec_launch_wide(t_loc, t_scale, p_loc, p_scale, gather_idx, block_offsets, nb, (int)max_block_dim, omega, S, B, seed,
+                                out_indices, max_aux, out_n_aux, out_status, out_sample, workspace, s);
+    }
     if (workspace_bytes < irec_beam_encode_workspace_bytes(nb, max_block_dim, S, B, max_aux))
         return irec_fail(IREC_E_CAPACITY, "beam_encode: workspace too small");
-    if (!(omega > 0.f)) return irec_fail(IREC_E_INVALID, "beam_encode: kl_per_partition must be > 0");
 
     const int rchoice = resident_choice();
     const int cluster_G = (irec_force_general() || rchoice != 0) ? 0 : irec_cluster_choice(nb, (int)max_block_dim, S, B);

@@ -49,6 +49,15 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
                      int2* hist, float* sched, int* work_counter, const int32_t* order, const void* plan, const void* tab, int tab_aux,
                      const void* tab_priv, cudaStream_t s);
 
+// irec_wide.cu: 32 < n_beams <= IREC_WIDE_MAX_BEAMS (beams, scores and history in global memory, radix-select top-B)
+#define IREC_WIDE_MAX_BEAMS 1024
+bool irec_wide_supported(int nb, int max_D, int S, int B);
+size_t irec_wide_workspace_bytes(int nb, int max_D, int S, int B, int max_aux);
+int irec_launch_wide(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
+                     const int64_t* gidx, const int64_t* offs, int nb, int max_D, float omega, int S, int B, int64_t seed,
+                     int32_t* out_indices, int max_aux, int32_t* out_n_aux, int32_t* out_status, float* out_sample,
+                     void* workspace, cudaStream_t s);
+
 #define IREC_ENSURE_INIT()                     \
     do {                                       \
         const int rc_init_ = irec_init();      \

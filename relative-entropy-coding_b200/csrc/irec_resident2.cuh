@@ -27,8 +27,17 @@
 #define R2_TOPK_CAP 1024
 
 // byte offset (into T2) of stream word u:  4 * dlog(1 + u mod 10006)   (beam_search_coder.py:39-43)
+// DLS: `dl4` is a copy of the table in SHARED memory.  A warp's 32 lookups are random 2-byte reads of a 20 KB table: from
+// global memory they touch ~27 different 128-byte lines (as many L1 wavefronts on the data pipe the quantile gathers need),
+// from shared memory ~3.5 (random banks).  Used by the general path, whose exponents are computed in place.
+template <bool DLS = false>
 __device__ __forceinline__ uint32_t r2_exp4(const uint16_t* __restrict__ dl4, uint32_t u)
 {
+    if (DLS) {
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"((uint32_t)__cvta_generic_to_shared(dl4 + u % IREC_ORD)));
+        return (uint32_t)v;
+    }
     return (uint32_t)__ldg(dl4 + u % IREC_ORD);
 }
 
@@ -61,7 +70,26 @@ struct R2Group {   // beams per inner batch: G * 4 independent gathers in flight
 //   j_base[k] = s_k * D + first dim of the chunk;  q0 = float4 index of the chunk's first quad
 //   row[k]: sample s_k's row of the precomputed exponent table (4 x uint16 per quad, CI layout) or nullptr
 //           (then the exponents come from Philox + dl4 in place)
-template <int BMAX, int NS, bool TAB, bool SPREAD = false, bool PACK = false>   // SPREAD: in-place two-choice bank assignment (TAB == false only); PACK: FP32x2 arithmetic
+// in-place exponents of quad iq for the NS samples of a lane (Philox -> uniform int -> discrete log [-> bank assignment])
+template <int NS, bool SPREAD, bool DLS>
+__device__ __forceinline__ void r2_exps_in_place(const uint16_t* __restrict__ dl4, const TfStream& st, const uint64_t (&j_base)[NS],
+                                                 int iq, uint32_t (&ad)[NS][4])
+{
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const uint64_t j = j_base[k] + 4 * iq;
+        const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
+        ad[k][0] = r2_exp4<DLS>(dl4, u.x); ad[k][1] = r2_exp4<DLS>(dl4, u.y);
+        ad[k][2] = r2_exp4<DLS>(dl4, u.z); ad[k][3] = r2_exp4<DLS>(dl4, u.w);
+        if (SPREAD) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ad[k][e] = r2_spread_banks(ad[k][e]);
+        }
+    }
+}
+
+// SPREAD: in-place two-choice bank assignment (TAB == false only); PACK: FP32x2 arithmetic; DLS: dl4 in shared memory
+template <int BMAX, int NS, bool TAB, bool SPREAD = false, bool PACK = false, bool DLS = false>
 __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, const uint16_t* __restrict__ dl4,
                                                const uint32_t* __restrict__ cb4,
                                                const float4* __restrict__ sa4, const float4* __restrict__ A4,
@@ -90,17 +118,7 @@ __device__ __forceinline__ void r2_score_chunk(const char* __restrict__ T2b, con
                 for (int k = 0; k < NS; ++k) nxt[k] = __ldg(tab_t + row[k] + (iq + 1) * P);
             }
         } else {
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                const uint64_t j = j_base[k] + 4 * iq;
-                const uint4 u = ((j & 3) == 0) ? tf_stream_group(st, j >> 2) : tf_stream_quad_at(st, j);
-                ad[k][0] = r2_exp4(dl4, u.x); ad[k][1] = r2_exp4(dl4, u.y);
-                ad[k][2] = r2_exp4(dl4, u.z); ad[k][3] = r2_exp4(dl4, u.w);
-                if (SPREAD) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ad[k][e] = r2_spread_banks(ad[k][e]);
-                }
-            }
+            r2_exps_in_place<NS, SPREAD, DLS>(dl4, st, j_base, iq, ad);
         }
         const int qi = q0 + iq * P;
         const float4 sa = sa4[qi], A = A4[qi], E = E4[qi], M = M4[qi];

@@ -146,6 +146,53 @@ def test_beam_resident_vs_oracle(cuda, case, kernel):
         run_beam_case(cuda, *case)
 
 
+WIDE_CASES = [
+    # recipe, D, data_seed, omega, extra, B, seed          n_beams > 32: k_beam_encode_wide (csrc/irec_wide.cu)
+    ("c1", 64, 0, 3.0, 1.2, 33, 42),         # one more than the persistent kernels take
+    ("c2", 192, 2, 3.0, 1.2, 64, 42),
+    ("c2", 1000, 1, 3.0, 1.2, 100, 42),      # a full C2 coder-block, B not a multiple of the scoring page
+    ("c2", 257, 9, 2.0, 1.0, 300, 5),        # S = 7: the beam count grows 1 -> 7 -> 49 -> 300
+    ("c3", 288, 3, 3.0, 1.0, 1024, 7),       # the largest beam width (S = 20: 1 -> 20 -> 400 -> 1024)
+    ("c2", 37, 6, 4.0, 1.3, 40, 1),          # unaligned Philox quads
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=[f"{c[0]}-D{c[1]}-B{c[5]}" for c in WIDE_CASES])
+def test_beam_wide_vs_oracle(cuda, case):
+    """n_beams > 32 (the reference has no limit, beam_search_coder.py:15-30): beams, scores and history in global memory,
+    radix-select top-B -- indices, sample bits and decode identical to the oracle"""
+    from irec_b200 import native as N
+    S = int(np.exp(case[3] * case[4]))
+    assert N.lib().irec_beam_encode_path(1, case[1], S, case[5]) == 4
+    run_beam_case(cuda, *case)
+
+
+def test_beam_wide_batch_ragged(cuda):
+    """several coder-blocks of different sizes in one wide-beam launch (persistent CTAs over the block queue)"""
+    import torch
+    from irec_b200 import engine
+    sizes = [100, 200, 37, 1000, 200, 5]
+    B, omega, S, seed = 48, 3.0, 36, 42
+    arrs = [synth.c2(n, data_seed=40 + i) for i, n in enumerate(sizes)]
+    flat = [torch.from_numpy(np.concatenate([a[k] for a in arrs])).to(cuda) for k in range(4)]
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=cuda)
+    out = engine.beam_encode_blocks(*flat, None, offsets, len(sizes), max(sizes), omega, S, B, seed)
+    smp = out.sample.cpu().numpy()
+    lo = 0
+    for b, (n, a) in enumerate(zip(sizes, arrs)):
+        ref = O.beam_encode_block(*a, omega, S, B, seed)
+        assert out.indices[b] == ref["indices"].tolist()
+        assert np.array_equal(bits(smp[lo:lo + n]), bits(ref["sample"]))
+        lo += n
+
+
+def test_beam_too_wide_is_an_error(cuda):
+    """beyond the wide kernel's range the call fails loudly (no fallback)"""
+    from irec_b200 import native as N
+    assert N.lib().irec_beam_encode_path(1, 64, 36, 1025) == 0
+    assert N.lib().irec_beam_encode_path(1, 2000, 36, 64) == 0
+
+
 @pytest.mark.parametrize("kernel", ["resident2", "tmem", "cluster8", "cluster4"])
 def test_beam_ragged_blocks_one_launch(cuda, kernel):
     """four different block sizes in ONE launch: two get a per-launch exponent table, the others generate their
