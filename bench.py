@@ -313,7 +313,8 @@ def bench_c5(ctx, args):
     return {"workload": "BASELINE configs[4]: one coder-block (D=64 posterior vs N(0,I)), candidate index range split over the "
                         "ranks, top-B records exchanged and merged per auxiliary variable",
             "n_gpus": world, "sweep": out,
-            "roofline": {"bound": "issue", "kernel": "k_gp_score_topb2<20>", "at_omega_bits": top["omega_bits"],
+            "roofline": {"bound": "issue", "kernel": "k_gp_fused<20>" if "k_gp_fused" in top["launch"] else "k_gp_score_topb2<20>",
+                         "at_omega_bits": top["omega_bits"],
                          "achieved": top["candidate_dims_per_sec"] * w / 1e9, "peak": peak / 1e9, "unit": "G lane-instr/s",
                          "frac": top["candidate_dims_per_sec"] * w / peak,
                          "work_model": "W = 10 + 24/B' lane-instr per candidate-dim, peak = N x SMs x 128 lanes x sm_max_mhz"}}

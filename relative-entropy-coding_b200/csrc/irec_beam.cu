@@ -559,16 +559,33 @@ struct Score2Args {
     irec_record_t* out_rec; int32_t* out_cnt;
     int cand_cap;
 };
+// Slot in a shared-memory list for the lanes of a warp that have something to append: ONE atomicAdd per warp (same-address
+// shared atomics serialise: the first scoring round of a variable appends every candidate, 7680 atomics -- 12 % of the warp
+// samples of k_gp_fused in profiles/r2_gp_fused_b_ncu.md).  All 32 lanes must call it; returns -1 for lanes with pass == false.
+__device__ __forceinline__ int warp_append_pos(int32_t* cnt, bool pass)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0u) return -1;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pass ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+// Candidate buffer of a CTA: everything that beats `tau` (the B-th best score at the last compaction) is appended; the buffer
+// is compacted to its best B (exact block_topk) only when more than GP2_SLACK entries have piled up, not after every round --
+// after the first rounds of a variable a round adds a handful of entries, and a compaction costs several CTA barriers
+// (block_topk held 41 % of the warp samples of k_gp_fused when it ran after every round).  Capacity: one full round + GP2_SLACK.
+#define GP2_SLACK 512
 struct Gp2Sink {
     float* s_csc; int32_t* s_cid; int32_t* s_cnt;
     float tau; int Bcur, boff; int s_hi;      // s_hi: first sample beyond this CTA's range
-    __device__ __forceinline__ void operator()(int sk, int b, float x, bool dup) const
+    __device__ __forceinline__ void operator()(int sk, int b, float x, bool dup) const      // called by all 32 lanes of a warp
     {
         b += boff;
-        if (dup || b >= Bcur || sk >= s_hi) return;
         const float v = (x == x) ? x : __int_as_float(0xff800000);
-        if (v >= tau) {
-            const int pos = atomicAdd(s_cnt, 1);
+        const int pos = warp_append_pos(s_cnt, !dup && b < Bcur && sk < s_hi && v >= tau);
+        if (pos >= 0) {
             s_csc[pos] = v;
             s_cid[pos] = sk * Bcur + b;
         }
@@ -665,7 +682,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_score_topb2(const Score2A
         }
         __syncthreads();
         const int cnt = *s_cnt;
-        if (cnt > B) {
+        if (cnt > GP2_SLACK) {                     // room for the next full round must remain: cap = round + GP2_SLACK
             const int Kout = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
             if (tid < Kout) { s_csc[tid] = s_wsc[tid]; s_cid[tid] = s_wid[tid]; }
             if (tid == 0) { *s_cnt = Kout; if (Kout == B) *s_tau = s_wsc[Kout - 1]; }
@@ -949,7 +966,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             }
             __syncthreads();
             const int cnt = *s_cnt;
-            if (cnt > B) {
+            if (cnt > GP2_SLACK) {                 // lazy compaction (Gp2Sink)
                 const int Kc = block_topk(s_csc, s_cid, cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
                 if (tid < Kc) { s_csc[tid] = s_wsc[tid]; s_cid[tid] = s_wid[tid]; }
                 if (tid == 0) { *s_cnt = Kc; if (Kc == B) *s_tau = s_wsc[Kc - 1]; }
@@ -983,10 +1000,13 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             // merge scratch: the CTA's own candidate buffer (free at this point) when the lists fit, else global memory
             float* m_sc = ((int)gridDim.x * B <= cap && a.world * B <= cap) ? s_csc : a.g_sc;
             int32_t* m_id = (m_sc == s_csc) ? s_cid : a.g_id;
-            for (int i = tid; i < (int)gridDim.x * B; i += nt) {
+            const int n_rec = (int)gridDim.x * B;
+            for (int i0 = 0; i0 < n_rec; i0 += nt) {                  // whole warps stay in the loop (warp_append_pos)
+                const int i = i0 + tid;
                 const int li = i / B, e = i - li * B;
-                if (e < __ldcg(a.list_cnt + li)) {
-                    const int pos = atomicAdd(s_cnt, 1);
+                const bool have = i < n_rec && e < __ldcg(a.list_cnt + li);
+                const int pos = warp_append_pos(s_cnt, have);
+                if (pos >= 0) {
                     const int4 v = __ldcg(reinterpret_cast<const int4*>(a.lists) + i);      // (score bits, s, b, pad) straight from L2
                     m_sc[pos] = __int_as_float(v.x);
                     m_id[pos] = v.y * Bcur + v.z;
@@ -1481,7 +1501,7 @@ static size_t gp2_score_smem(int cand_cap)
 static int gp2_cand_cap(int D, int bmax)
 {
     const BeamGeom g = make_geom(D);
-    return (GP2_THREADS / 32) * GP2_NS * g.SPW * bmax + 64;
+    return (GP2_THREADS / 32) * GP2_NS * g.SPW * bmax + GP2_SLACK;
 }
 static int gp2_score_grid(int D, int64_t n_samples)
 {
