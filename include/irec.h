@@ -116,7 +116,8 @@ size_t irec_beam_encode_workspace_bytes(int nb, int64_t max_block_dim, int S, in
  * per partition, B = n_beams, omega = kl_per_partition (nats), coding seed `seed` (partition t of
  * every block uses seed+t).  Outputs: out_indices [nb x max_aux] (partition order, first n_aux[b]
  * valid), out_n_aux [nb], out_status [nb] (IREC_BLK_*), out_sample [N] (= beam[0] + p_loc,
- * scattered through gather_idx). */
+ * scattered through gather_idx).  1 <= B <= 1024 (the reference has no limit; B > 32 takes k_beam_encode_wide and needs
+ * max_block_dim <= 1024), S * B < 2^31; IREC_E_CAPACITY otherwise. */
 int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_loc, const float* p_scale,
                      const int64_t* gather_idx, const int64_t* block_offsets, int nb, int64_t max_block_dim,
                      float omega, int S, int B, int64_t seed,
@@ -125,7 +126,9 @@ int irec_beam_encode(const float* t_loc, const float* t_scale, const float* p_lo
 
 /* Which kernel irec_beam_encode runs for these sizes on the current device (diagnostics, tests, bench reports):
  * 0 = one partition per launch (general path), 1 = k_beam_encode_resident, 2 = k_beam_encode_resident2 (persistent CTA per
- * coder-block), 3 = k_beam_encode_tmem (beams and coefficients in tensor memory, two coder-blocks per SM), 100 + G = k_beam_encode_cluster with G CTAs per coder-block (few blocks per launch: one image). */
+ * coder-block), 3 = k_beam_encode_tmem (beams and coefficients in tensor memory, two coder-blocks per SM), 4 = k_beam_encode_wide
+ * (n_beams > 32), 100 + G = k_beam_encode_cluster with G CTAs per coder-block (few blocks per launch: one image).  For B > 32
+ * a return of 0 means "not supported". */
 int irec_beam_encode_path(int nb, int64_t max_block_dim, int S, int B);
 
 /* BeamSearchCoder.decode_block over nb blocks (beam_search_coder.py:124-148).  indices
