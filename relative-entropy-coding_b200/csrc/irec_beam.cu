@@ -14,6 +14,9 @@
 #include "irec_host.h"
 #include <string.h>
 #include <mutex>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
 
 // =============================================================================================
 // k_kl_naux
@@ -845,7 +848,16 @@ struct FusedArgs {
     int32_t* sync;                   // [0] arrivals, [1] published sequence (both zeroed before the launch)
     int32_t* const* peer_bufs; int rank, world;   // nullptr / 0 / 1 on a single GPU
     int cand_cap;
+    long long* prof;                 // diagnostics (IREC_GP_PROFILE=1): [grid][8] phase cycles of thread 0, or nullptr
 };
+#define GPF_TICK(slot)                                                        \
+    do {                                                                      \
+        if (a.prof && tid == 0) {                                             \
+            const long long now_ = clock64();                                 \
+            a.prof[(size_t)blockIdx.x * 8 + (slot)] += now_ - prof_t;         \
+            prof_t = now_;                                                    \
+        }                                                                     \
+    } while (0)
 
 template <int BMAX>
 __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
@@ -907,6 +919,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
     const int64_t s_hi64 = min(a.s_end, a.s_begin + sg1 * g.SPW);
     const int s_hi = (int)s_hi64;
     int Bcur = 1, cur = 0;
+    long long prof_t = a.prof ? clock64() : 0;
 
     for (int t = 0; t < n_aux; ++t) {
         // ---- schedule of this auxiliary variable (every CTA for itself) ----
@@ -922,6 +935,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
         if (tid < 32) s_cb[tid] = tid < Bcur ? (uint32_t)__ldg(a.dl4 + (hash_from_sum(hs[tid]) - 1)) : 0u;
         if (tid == 0) { *s_cnt = 0; *s_tau = __int_as_float(0xff800000); }
         __syncthreads();
+        GPF_TICK(0);                                                 // schedule
         const float4* sa4 = reinterpret_cast<const float4*>(s_sa);
         const float4* A4 = reinterpret_cast<const float4*>(s_A);
         const float4* E4 = reinterpret_cast<const float4*>(s_E);
@@ -974,6 +988,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             }
         }
         __syncthreads();
+        GPF_TICK(1);                                                 // scoring rounds (with their compactions)
         const int Kcta = block_topk(s_csc, s_cid, *s_cnt, B, s_wsc, s_wid, s_gmax, s_list, TOPK_CAP, s_ctl);
 
         // ---- publish, arrive; the last CTA merges, exchanges, publishes the winners ----
@@ -991,6 +1006,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             s_flag[0] = (ticket == (t + 1) * (int)gridDim.x - 1) ? 1 : 0;
         }
         __syncthreads();
+        GPF_TICK(2);                                                 // the CTA's own top-B, publish, arrive
         const int parity = t & 1;
         if (s_flag[0]) {
             __threadfence();
@@ -1070,6 +1086,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             __threadfence();
             __syncthreads();
             if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sync + 1), "r"(t + 1) : "memory");
+            GPF_TICK(3);                                             // last arriver: merge + exchange + publish
         }
         if (tid == 0) {
             int got;
@@ -1078,6 +1095,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             } while (got < t + 1);
         }
         __syncthreads();
+        GPF_TICK(4);                                                 // waiting for the winners
         const int K = __ldcg(a.nwin + parity);
         if (tid < K) {
             const int4 v = __ldcg(reinterpret_cast<const int4*>(a.win + parity * 32) + tid);
@@ -1117,6 +1135,7 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             }
         }
         __syncthreads();
+        GPF_TICK(5);                                                 // commit
         Bcur = K;
         cur ^= 1;
     }
@@ -1928,6 +1947,15 @@ int irec_beam_encode_fused(void* state, int D, int B, int64_t s_begin, int64_t s
     a.g_id = reinterpret_cast<int32_t*>(a.g_sc + (gsz + (size_t)world) * 32 + 64);
     a.peer_bufs = reinterpret_cast<int32_t* const*>(peer_bufs); a.rank = rank; a.world = world; a.cand_cap = cap;
     if (cudaMemsetAsync(a.sync, 0, 256, s) != cudaSuccess) return irec_fail(IREC_E_CUDA, "beam_encode_fused: memset failed");
+    a.prof = nullptr;
+    static long long* d_prof = nullptr;            // diagnostics only (IREC_GP_PROFILE=1): phase cycle counters, dumped to stderr
+    const char* pe = getenv("IREC_GP_PROFILE");
+    const bool prof_on = pe && pe[0] == '1';
+    if (prof_on) {
+        if (!d_prof) cudaMalloc(&d_prof, sizeof(long long) * 8 * 1024);
+        cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * 1024, s);
+        a.prof = d_prof;
+    }
     int rc = IREC_E_INVALID;
     switch (bmax) {
         case 1: rc = launch_fused_t<1>(a, grid, smem, s); break;
@@ -1940,6 +1968,17 @@ int irec_beam_encode_fused(void* state, int D, int B, int64_t s_begin, int64_t s
         case 32: rc = launch_fused_t<32>(a, grid, smem, s); break;
     }
     if (rc != IREC_OK) { cudaGetLastError(); return irec_fail(rc, "beam_encode_fused: cooperative launch failed"); }
+    if (prof_on) {
+        std::vector<long long> h((size_t)8 * grid);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double tot[8] = { 0 };
+        for (int i = 0; i < grid; ++i)
+            for (int k = 0; k < 8; ++k) tot[k] += (double)h[(size_t)i * 8 + k];
+        fprintf(stderr, "[gp profile] rank %d grid %d, cycles per CTA over the launch: schedule %.0f scoring %.0f own-topB+arrive %.0f "
+                        "waiting %.0f commit %.0f | last arriver (sum over variables): merge+exchange+publish %.0f\n", rank, grid,
+                tot[0] / grid, tot[1] / grid, tot[2] / grid, tot[4] / grid, tot[5] / grid, tot[3]);
+    }
     return irec_check_launch("k_gp_fused");
 }
 
