@@ -15,6 +15,7 @@
 #include <string.h>
 #include <mutex>
 #include <vector>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -562,19 +563,6 @@ struct Score2Args {
     irec_record_t* out_rec; int32_t* out_cnt;
     int cand_cap;
 };
-// Slot in a shared-memory list for the lanes of a warp that have something to append: ONE atomicAdd per warp (same-address
-// shared atomics serialise: the first scoring round of a variable appends every candidate, 7680 atomics -- 12 % of the warp
-// samples of k_gp_fused in profiles/r2_gp_fused_b_ncu.md).  All 32 lanes must call it; returns -1 for lanes with pass == false.
-__device__ __forceinline__ int warp_append_pos(int32_t* cnt, bool pass)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (m == 0u) return -1;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(cnt, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return pass ? base + __popc(m & ((1u << lane) - 1u)) : -1;
-}
 // Candidate buffer of a CTA: everything that beats `tau` (the B-th best score at the last compaction) is appended; the buffer
 // is compacted to its best B (exact block_topk) only when more than GP2_SLACK entries have piled up, not after every round --
 // after the first rounds of a variable a round adds a handful of entries, and a compaction costs several CTA barriers
@@ -948,13 +936,17 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
         //      a round of clamped duplicates would double the work ----
         for (int64_t base = sg0; base < sg1; base += (int64_t)nwarps * GP2_NS) {
             const float tau = *s_tau;
-            if (base + warp < sg1) {
-                uint64_t jb[GP2_NS];
-                uint32_t row[GP2_NS];
+            // A warp scores GP2_NS sample groups of the round when all of them exist, otherwise only its first one (the tail
+            // round of a variable: with ~30 groups per CTA -- S = 6e5 over 8 GPUs -- scoring a clamped duplicate as the second
+            // group doubled the tail round's work)
+            auto score_round = [&](auto ns_c) {
+                constexpr int NS = decltype(ns_c)::value;
+                uint64_t jb[NS];
+                uint32_t row[NS];
 #pragma unroll
-                for (int k = 0; k < GP2_NS; ++k) {
+                for (int k = 0; k < NS; ++k) {
                     const int64_t s = a.s_begin + (base + warp + (int64_t)k * nwarps) * g.SPW + lane / g.P;
-                    const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // groups beyond the range: clamped, not stored
+                    const uint64_t s_eff = (uint64_t)(s < s_hi64 ? s : a.s_begin);          // samples beyond the range: clamped, not stored
                     jb[k] = s_eff * (uint64_t)g.D + (uint64_t)(32 * lg);
                     row[k] = 0u;
                 }
@@ -962,22 +954,24 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
 #pragma unroll 1
                 for (int boff = 0; boff < BMAX; boff += HB) {
                     if (boff >= Bcur) break;
-                    float acc[GP2_NS][HB];
+                    float acc[NS][HB];
 #pragma unroll
-                    for (int k = 0; k < GP2_NS; ++k)
+                    for (int k = 0; k < NS; ++k)
 #pragma unroll
                         for (int b = 0; b < HB; ++b) acc[k][b] = 0.f;
-                    r2_score_chunk<HB, GP2_NS, false, GP2_SPREAD, false, true>(T2b, s_dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
-                                                                               g.P, lg, st, jb, nullptr, row, acc);
-                    float v[GP2_NS * HB];
+                    r2_score_chunk<HB, NS, false, GP2_SPREAD, false, true>(T2b, s_dl4, s_cb + boff, sa4, A4, E4, M4, beams4 + boff * nq, nq,
+                                                                           g.P, lg, st, jb, nullptr, row, acc);
+                    float v[NS * HB];
 #pragma unroll
-                    for (int k = 0; k < GP2_NS; ++k)
+                    for (int k = 0; k < NS; ++k)
 #pragma unroll
                         for (int b = 0; b < HB; ++b) v[k * HB + b] = acc[k][b];
                     const Gp2Sink sink{ s_csc, s_cid, s_cnt, tau, Bcur, boff, s_hi };
-                    r2_tree_store<GP2_NS * HB, GP2_NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
+                    r2_tree_store<NS * HB, NS * HB, HB, 0, Gp2Sink>(v, g.P, lane, s_first, nwarps * g.SPW, sink);
                 }
-            }
+            };
+            if (base + warp + (int64_t)(GP2_NS - 1) * nwarps < sg1) score_round(std::integral_constant<int, GP2_NS>{});
+            else if (base + warp < sg1) score_round(std::integral_constant<int, 1>{});
             __syncthreads();
             const int cnt = *s_cnt;
             if (cnt > GP2_SLACK) {                 // lazy compaction (Gp2Sink)
@@ -1016,16 +1010,28 @@ __global__ void __launch_bounds__(GP2_THREADS, 1) k_gp_fused(const FusedArgs a)
             // merge scratch: the CTA's own candidate buffer (free at this point) when the lists fit, else global memory
             float* m_sc = ((int)gridDim.x * B <= cap && a.world * B <= cap) ? s_csc : a.g_sc;
             int32_t* m_id = (m_sc == s_csc) ? s_cid : a.g_id;
+            // The record loads are issued four rounds at a time BEFORE anything depends on them: the loop used to pay two
+            // dependent L2 round trips (count, then record) per round of 384 records -- half of the 11 us this merge took per
+            // variable (IREC_GP_PROFILE).  Unpublished slots of a list are skipped by their position (e >= count).
             const int n_rec = (int)gridDim.x * B;
-            for (int i0 = 0; i0 < n_rec; i0 += nt) {                  // whole warps stay in the loop (warp_append_pos)
-                const int i = i0 + tid;
-                const int li = i / B, e = i - li * B;
-                const bool have = i < n_rec && e < __ldcg(a.list_cnt + li);
-                const int pos = warp_append_pos(s_cnt, have);
-                if (pos >= 0) {
-                    const int4 v = __ldcg(reinterpret_cast<const int4*>(a.lists) + i);      // (score bits, s, b, pad) straight from L2
-                    m_sc[pos] = __int_as_float(v.x);
-                    m_id[pos] = v.y * Bcur + v.z;
+            for (int i0 = 0; i0 < n_rec; i0 += 4 * nt) {              // whole warps stay in the loop (warp_append_pos)
+                int4 v[4];
+                bool have[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 + k * nt + tid;
+                    const int li = i / B, e = i - li * B;
+                    have[k] = i < n_rec && e < __ldcg(a.list_cnt + li);
+                    v[k] = make_int4(0, 0, 0, 0);
+                    if (i < n_rec) v[k] = __ldcg(reinterpret_cast<const int4*>(a.lists) + i);   // (score bits, s, b, pad) straight from L2
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pos = warp_append_pos(s_cnt, have[k]);
+                    if (pos >= 0) {
+                        m_sc[pos] = __int_as_float(v[k].x);
+                        m_id[pos] = v[k].y * Bcur + v[k].z;
+                    }
                 }
             }
             __syncthreads();

@@ -249,6 +249,19 @@ __device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch, const 
 }
 __device__ __forceinline__ double block_tree_sum_f64(double* cs, int nch) { return block_tree_sum_f64(cs, nch, CtaGroup{}); }
 
+// Slot in a shared-memory list for the lanes of a warp that have something to append: ONE atomicAdd per warp (same-address
+// shared atomics serialise: the first scoring round of a variable appends every candidate, 7680 atomics -- 12 % of the warp
+// samples of k_gp_fused in profiles/r2_gp_fused_b_ncu.md).  All 32 lanes must call it; returns -1 for lanes with pass == false.
+__device__ __forceinline__ int warp_append_pos(int32_t* cnt, bool pass)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0u) return -1;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pass ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
 // ---------------------------------------------------------------------------------------------
 // block_topk: out[0..Kout) = the Kout = min(K, n) best of n candidates, best first, by
 // (score desc, id asc).  sc/id may live in shared or global memory; id == nullptr means id = i.
@@ -291,12 +304,11 @@ __device__ __forceinline__ int block_topk(const float* sc, const int32_t* id, in
     grp.sync();
     const float tau = __int_as_float(s_ctl[1]);
 
-    // 2. survivors
-    for (int i = tid; i < n; i += nt) {
-        if (sc[i] >= tau) {
-            const int pos = atomicAdd(&s_ctl[0], 1);
-            if (pos < cap) s_list[pos] = i;
-        }
+    // 2. survivors (one shared atomic per warp: whole warps stay in the loop)
+    for (int i0 = 0; i0 < n; i0 += nt) {
+        const int i = i0 + tid;
+        const int pos = warp_append_pos(&s_ctl[0], i < n && sc[i] >= tau);
+        if (pos >= 0 && pos < cap) s_list[pos] = i;
     }
     grp.sync();
     const int ns = s_ctl[0];
