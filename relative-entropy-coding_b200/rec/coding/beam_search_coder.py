@@ -13,6 +13,22 @@ from rec.coding.coder import GaussianCoder, _dist_tensors
 from rec.coding.utils import CodingError
 
 
+class _LazyIndices:
+    """callable returned by encode_batch(lazy=True): reads the index lists back on demand.  `retried` (valid after the call)
+    tells a pipelining caller that the launch had to be repeated with more index rows -- the sample tensor it handed to
+    later launches before this call returned was not final (engine.PendingBeamResult)."""
+
+    def __init__(self, pend, nest):
+        self._pend, self._nest = pend, nest
+
+    def __call__(self):
+        return self._nest(self._pend.indices())
+
+    @property
+    def retried(self):
+        return bool(self._pend.retried)
+
+
 class BeamSearchCoder(GaussianCoder):
 
     def __init__(self, kl_per_partition, n_beams, extra_samples=1., extrapolate_auxiliary_ratios=True,
@@ -116,7 +132,7 @@ class BeamSearchCoder(GaussianCoder):
             with self._ratios_ctx(tl.device):
                 pend = E.beam_encode_blocks(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), gather, offsets,
                                             nb, max_dim, self.kl_per_partition, self.n_samples, self.n_beams, seed, lazy=True)
-            return (lambda: nest(pend.indices())), pend.sample.reshape(shape)
+            return _LazyIndices(pend, nest), pend.sample.reshape(shape)
         indices, sample = self._encode_flat(tl.reshape(-1), ts.reshape(-1), pl.reshape(-1), ps.reshape(-1), gather,
                                             offsets, nb, max_dim, seed)
         return nest(indices), sample.reshape(shape)

@@ -77,6 +77,91 @@ class LatentHierarchy:
         return latents
 
 
+    # -- a batch of images (BASELINE.json configs[3]) ----------------------------------------------------------------
+    @staticmethod
+    def _sub_batches(n_images, n_streams):
+        """image ranges coded as independent pipelines, each on its own stream.  Default 1: with pre-resident inputs two
+        sub-batches fill each other's launch tails (bench.py at 128 images per GPU: +13 %), but here every
+        level also enqueues the ladder's small kernels, which cannot start on an SM a persistent coder CTA occupies (it holds
+        the whole register file) -- bench_batch.py, 128 images x 24 levels: 680 ms with one stream, 650-790 ms with two."""
+        k = max(1, min(int(n_streams or 1), n_images))
+        return [(i * n_images // k, (i + 1) * n_images // k) for i in range(k)]
+
+    def compress_batch(self, seed, coder, n_streams=None, _again=True):
+        """every image of a batched ladder (`ladder.n_images`; `ladder.prior(level, latents, lo, hi)` with loc/scale of shape
+        [hi - lo, ...]) through all levels: what looping `compress` over the images computes, as ONE launch per level and
+        sub-batch (`coder.encode_batch(lazy=True)`).  The levels of an image are sequential (its next prior needs its latent),
+        the images are not: the batch is cut into `n_streams` sub-batches, each running its own level sequence on its own
+        CUDA stream without host synchronisation; the index lists are read back at the end.
+        Returns (block_indices[image][level][block], latents[level] of shape [n_images, ...])."""
+        n_images, n_levels = self.ladder.n_images, self.ladder.n_levels
+        dev = self.ladder.device
+        subs = self._sub_batches(n_images, n_streams)
+        cur = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in subs] if len(subs) > 1 else [cur]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        state = [{"latents": []} for _ in subs]
+        block_indices = [[None] * n_levels for _ in range(n_images)]
+        wrap = coder.block_size is None
+
+        retried = []
+
+        def drain(level, pending):
+            """index lists of a level: built on the host while the NEXT level runs on the device"""
+            for (lo, hi), get_indices in zip(subs, pending):
+                per_item = get_indices()
+                retried.append(bool(getattr(get_indices, "retried", False)))
+                for i in range(hi - lo):
+                    block_indices[lo + i][level] = [per_item[i]] if wrap else per_item[i]
+
+        previous = None
+        for level in range(n_levels):
+            pending = []
+            for (lo, hi), st, stream in zip(subs, state, streams):
+                with torch.cuda.stream(stream):
+                    if level == 0 and stream is not cur:
+                        stream.wait_event(fork)
+                    prior = self.ladder.prior(level, st["latents"], lo, hi)
+                    posterior = self.ladder.posterior(level, st["latents"], lo, hi)
+                    get_indices, latent = coder.encode_batch(posterior, prior, seed=seed, lazy=True)
+                    st["latents"].append(latent)
+                    pending.append(get_indices)
+            if previous is not None:
+                drain(level - 1, previous)
+            previous = pending
+        drain(n_levels - 1, previous)
+        for stream in streams:
+            if stream is not cur:
+                cur.wait_stream(stream)
+        if any(retried):
+            # a launch ran out of index rows and was repeated AFTER later levels had consumed its latent: the row-capacity
+            # hint has grown meanwhile, so one more pass runs without repeats
+            if not _again:
+                raise RuntimeError("compress_batch: index-row capacity still too small on the second pass")
+            torch.cuda.synchronize(dev)
+            return self.compress_batch(seed, coder, n_streams=n_streams, _again=False)
+        latents = []
+        for level in range(n_levels):
+            parts = [st["latents"][level] for st in state]
+            for t in parts:
+                t.record_stream(cur)
+            latents.append(torch.cat(parts, dim=0) if len(parts) > 1 else parts[0])
+        return block_indices, latents
+
+    def decompress_batch(self, coder, block_indices, seed):
+        """replays the batched ladder from the index lists of `compress_batch`; returns latents[level] of shape [n_images, ...]"""
+        n_images = self.ladder.n_images
+        latents = []
+        for level in range(self.ladder.n_levels):
+            prior = self.ladder.prior(level, latents, 0, n_images)
+            idx = [[list(b) for b in block_indices[i][level]] for i in range(n_images)]
+            if coder.block_size is None:
+                idx = [item[0] for item in idx]
+            latents.append(coder.decode_batch(prior, idx, seed=seed))
+        return latents
+
+
 class SyntheticLadder:
     """Seeded synthetic stand-in for the networks (SURVEY.md 8d recipes): level shapes as given; the prior of level k is
     the recipe's prior shifted by a fixed random projection of the previous level's latent, the posterior is the recipe's
@@ -117,4 +202,40 @@ class SyntheticLadder:
         pl, ps, dz, rs, _ = self._base[level]
         shape = (1,) + self.shapes[level]
         mu_p = pl + self._shift(level, latents)
+        return Normal((mu_p + ps * dz).reshape(shape), (ps * rs).reshape(shape))
+
+
+class BatchedSyntheticLadder:
+    """`n_images` independent SyntheticLadders side by side (image i uses data_seed + i): prior / posterior return the rows
+    [lo, hi) of the batch, shape [hi - lo, ...]; `latents` are the previous levels' latents of the SAME rows.  Row i equals
+    SyntheticLadder(shapes, recipe, data_seed + i) bit for bit."""
+
+    def __init__(self, shapes, n_images, recipe="c2", data_seed=0, device="cuda", coupling=0.25):
+        self.shapes = [tuple(s) for s in shapes]
+        self.n_levels = len(self.shapes)
+        self.n_images = int(n_images)
+        self.device = device
+        self.coupling = float(coupling)
+        singles = [SyntheticLadder(shapes, recipe=recipe, data_seed=data_seed + i, device=device, coupling=coupling)
+                   for i in range(self.n_images)]
+        self._base = [[torch.stack([s._base[k][j] for s in singles]) for j in range(5)] for k in range(self.n_levels)]
+
+    def _shift(self, level, latents, lo, hi):
+        if level == 0 or not latents:
+            return 0.0
+        prev = latents[level - 1].reshape(hi - lo, -1)
+        mix = self._base[level][4][lo:hi] % prev.shape[1]
+        return self.coupling * torch.tanh(torch.gather(prev, 1, mix))
+
+    def prior(self, level, latents, lo=0, hi=None):
+        hi = self.n_images if hi is None else hi
+        pl, ps = self._base[level][0][lo:hi], self._base[level][1][lo:hi]
+        shape = (hi - lo,) + self.shapes[level]
+        return Normal((pl + self._shift(level, latents, lo, hi)).reshape(shape), ps.reshape(shape))
+
+    def posterior(self, level, latents, lo=0, hi=None):
+        hi = self.n_images if hi is None else hi
+        pl, ps, dz, rs, _ = (a[lo:hi] for a in self._base[level])
+        shape = (hi - lo,) + self.shapes[level]
+        mu_p = pl + self._shift(level, latents, lo, hi)
         return Normal((mu_p + ps * dz).reshape(shape), (ps * rs).reshape(shape))

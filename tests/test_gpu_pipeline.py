@@ -116,3 +116,33 @@ def test_pipelined_compress_equals_level_by_level(cuda, tmp_path):
     assert i1 == i2 and all(torch.equal(x, y) for x, y in zip(l1, l2))
     with pytest.raises(CodingError):
         model.compress(42, coder, max_aux=8)
+
+
+@pytest.mark.parametrize("block_size", [1000, None])
+def test_compress_batch_equals_per_image(cuda, block_size):
+    """BASELINE configs[3] as a pipeline with real level-to-level dependence: LatentHierarchy.compress_batch (one launch per
+    level and sub-batch, sub-batches on their own CUDA streams, no host synchronisation between levels) == looping `compress`
+    over the images, whatever the number of streams; decompress_batch replays it bit for bit"""
+    import torch
+    from rec.coding import BeamSearchCoder
+    from rec.models import BatchedSyntheticLadder, LatentHierarchy, SyntheticLadder
+    shapes = [(16, 16, 32)] * 3 if block_size else [(4, 4, 8)] * 3
+    n_images = 6
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=block_size)
+    batched = LatentHierarchy(BatchedSyntheticLadder(shapes, n_images, recipe="c2", data_seed=40, device=cuda))
+    ref_idx, ref_lat = [], []
+    for i in range(n_images):
+        single = LatentHierarchy(SyntheticLadder(shapes, recipe="c2", data_seed=40 + i, device=cuda))
+        bi, lat = single.compress(seed=42, coder=coder)
+        ref_idx.append(bi)
+        ref_lat.append(lat)
+    for n_streams in (1, 2, 3, None):
+        idx, lat = batched.compress_batch(seed=42, coder=coder, n_streams=n_streams)
+        torch.cuda.synchronize()
+        assert idx == ref_idx, f"n_streams={n_streams}: index lists differ from the per-image loop"
+        for level in range(len(shapes)):
+            for i in range(n_images):
+                assert torch.equal(lat[level][i], ref_lat[i][level][0]), (n_streams, level, i)
+    dec = batched.decompress_batch(coder, idx, seed=42)
+    for level in range(len(shapes)):
+        assert torch.equal(dec[level], lat[level])
