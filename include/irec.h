@@ -58,6 +58,12 @@ float irec_aux_ratio(int i);
  * more auxiliary variables than n reports IREC_BLK_TOO_LONG (the reference raises CodingError there,
  * coder.py:226-231). */
 int irec_set_thread_aux_ratios(const float* dev_ratios, int n);
+/* Streams: SMs that the persistent batch kernel of irec_beam_encode leaves free, for every later call made by the CALLING
+ * HOST THREAD (k < 0: back to the default, 0 or the environment variable IREC_RESERVE_SMS).  A CTA of that kernel occupies
+ * its SM completely; a caller that runs independent sub-batches on several streams (a level's launch of sub-batch A beside
+ * the small network kernels that prepare sub-batch B's next level) reserves a few SMs so that those kernels can start while
+ * a launch is running.  Results do not depend on it. */
+int irec_set_thread_reserved_sms(int k);
 /* HOST: number of auxiliary variables the ratio table in force for the calling thread covers (the learned table's
  * length, else the power-law table's 65536): an index list longer than this cannot be decoded (coder.py:226-231) */
 int irec_aux_ratio_len(void);

@@ -5,6 +5,8 @@
 #include <string.h>
 #include <atomic>
 #include <mutex>
+#include <algorithm>
+#include <cstdlib>
 
 #include "irec_common.cuh"
 #include "irec_host.h"
@@ -46,6 +48,14 @@ const IrecDevice& irec_device()
 static thread_local const float* tl_ratio = nullptr;
 static thread_local int tl_ratio_len = 0;
 const float* irec_ratio_tab() { return tl_ratio ? tl_ratio : irec_device().d_ratio; }
+// SMs the persistent batch kernels leave free for the calling thread's launches (include/irec.h: irec_set_thread_reserved_sms)
+static thread_local int tl_reserved_sms = -1;
+int irec_reserved_sms()
+{
+    if (tl_reserved_sms >= 0) return tl_reserved_sms;
+    const char* e = getenv("IREC_RESERVE_SMS");
+    return e ? std::max(0, atoi(e)) : 0;
+}
 int irec_ratio_len() { return tl_ratio ? tl_ratio_len : irec_device().ratio_len; }
 
 // ---------------------------------------------------------------------------------------------
@@ -132,6 +142,12 @@ int irec_set_thread_aux_ratios(const float* dev_ratios, int n)
     if ((dev_ratios == nullptr) != (n == 0) || n < 0) return irec_fail(IREC_E_INVALID, "irec_set_thread_aux_ratios: need (ptr, n > 0) or (NULL, 0)");
     tl_ratio = dev_ratios;
     tl_ratio_len = n;
+    return IREC_OK;
+}
+
+int irec_set_thread_reserved_sms(int k)
+{
+    tl_reserved_sms = k < 0 ? -1 : k;
     return IREC_OK;
 }
 

@@ -26,6 +26,7 @@ struct IrecDevice {
 const IrecDevice& irec_device();                   // tables of the CURRENT device (after irec_init)
 const float* irec_ratio_tab();                     // auxiliary variance ratios in force for the calling thread (device pointer)
 int irec_ratio_len();
+int irec_reserved_sms();                           // SMs the persistent batch kernels leave free (irec_set_thread_reserved_sms / IREC_RESERVE_SMS)
 int irec_fail(int code, const char* msg);          // records the message, returns code
 int irec_check_launch(const char* what);           // cudaGetLastError -> IREC_E_CUDA
 void irec_count_launch();

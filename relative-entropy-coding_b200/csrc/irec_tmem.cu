@@ -811,7 +811,11 @@ bool irec_tmem_plan(int nb, int max_D, int S, int B, TmemPlan* out)
         default: ok = false;
     }
     if (!ok) return false;
-    p.grid = std::max(1, std::min(nb, irec_device().sm_count));     // two contexts per CTA; see the queue policy in the kernel
+    // A CTA of this kernel holds the whole register file of its SM (512 threads x 128 registers): nothing else runs there until
+    // it retires.  A caller that pipelines sub-batches on several streams leaves a few SMs free (irec_set_thread_reserved_sms)
+    // so that the other streams' small kernels -- the callers' networks between two coder launches -- are not starved.
+    const int reserve = std::min(irec_reserved_sms(), irec_device().sm_count - 1);
+    p.grid = std::max(1, std::min(nb, irec_device().sm_count - reserve));     // two contexts per CTA; see the queue policy in the kernel
     if (out) *out = p;
     return true;
 }

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "irec_aux_ratio": (C.c_float, [_i32]),
     "irec_set_thread_aux_ratios": (C.c_int, [_vp, _i32]),
     "irec_aux_ratio_len": (C.c_int, []),
+    "irec_set_thread_reserved_sms": (C.c_int, [_i32]),
     "irec_tf_op_seed": (C.c_int64, [_i64]),
     "irec_split_permutation": (C.c_int, [_i64, _i64, _vp]),
     "irec_beam_uniform_int": (C.c_int, [_i64, _i64, _i64, _vp, _vp]),
@@ -167,6 +168,22 @@ class thread_aux_ratios:
             while _borrowed and _borrowed[0][0].query():
                 _borrowed.popleft()
             check(load_library().irec_set_thread_aux_ratios(None, 0), "irec_set_thread_aux_ratios")
+        return False
+
+
+class reserved_sms:
+    """`with reserved_sms(k):` -- the persistent batch kernels launched by this thread inside the block leave k SMs free, so
+    that small kernels of other streams can start while a launch is running (include/irec.h: irec_set_thread_reserved_sms)."""
+
+    def __init__(self, k):
+        self.k = int(k)
+
+    def __enter__(self):
+        check(load_library().irec_set_thread_reserved_sms(self.k), "irec_set_thread_reserved_sms")
+        return self
+
+    def __exit__(self, *exc):
+        check(load_library().irec_set_thread_reserved_sms(-1), "irec_set_thread_reserved_sms")
         return False
 
 

@@ -78,16 +78,22 @@ class LatentHierarchy:
 
 
     # -- a batch of images (BASELINE.json configs[3]) ----------------------------------------------------------------
+    RESERVED_SMS = 4      # SMs left to the ladder's small kernels when sub-batches run on several streams
+
     @staticmethod
-    def _sub_batches(n_images, n_streams):
-        """image ranges coded as independent pipelines, each on its own stream.  Default 1: with pre-resident inputs two
-        sub-batches fill each other's launch tails (bench.py at 128 images per GPU: +13 %), but here every
-        level also enqueues the ladder's small kernels, which cannot start on an SM a persistent coder CTA occupies (it holds
-        the whole register file) -- bench_batch.py, 128 images x 24 levels: 680 ms with one stream, 650-790 ms with two."""
-        k = max(1, min(int(n_streams or 1), n_images))
+    def _sub_batches(n_images, blocks_per_image, n_streams, device):
+        """image ranges coded as independent pipelines, each on its own stream: a launch of fewer than ~8 coder-blocks per block
+        context (two contexts per SM) is split in two, so that one launch's tail is filled by the next launch's head
+        (DESIGN.md section 5).  bench_batch.py, 128 images x 24 dependent levels on one B200: 683 ms with one stream, 615 ms
+        with two and 4 SMs reserved for the ladder's kernels (without the reserve: 640-770 ms, unstable -- a persistent coder
+        CTA holds the whole register file of its SM, so the other sub-batch's small kernels starve)."""
+        if n_streams is None:
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            n_streams = 2 if n_images * blocks_per_image <= 8 * 2 * sms else 1
+        k = max(1, min(int(n_streams), n_images))
         return [(i * n_images // k, (i + 1) * n_images // k) for i in range(k)]
 
-    def compress_batch(self, seed, coder, n_streams=None, _again=True):
+    def compress_batch(self, seed, coder, n_streams=None, _again=True, _reserve=True):
         """every image of a batched ladder (`ladder.n_images`; `ladder.prior(level, latents, lo, hi)` with loc/scale of shape
         [hi - lo, ...]) through all levels: what looping `compress` over the images computes, as ONE launch per level and
         sub-batch (`coder.encode_batch(lazy=True)`).  The levels of an image are sequential (its next prior needs its latent),
@@ -96,7 +102,13 @@ class LatentHierarchy:
         Returns (block_indices[image][level][block], latents[level] of shape [n_images, ...])."""
         n_images, n_levels = self.ladder.n_images, self.ladder.n_levels
         dev = self.ladder.device
-        subs = self._sub_batches(n_images, n_streams)
+        n0 = int(np.prod(self.ladder.shapes[0]))
+        per_image = 1 if coder.block_size is None else -(-n0 // coder.block_size)
+        subs = self._sub_batches(n_images, per_image, n_streams, dev)
+        if len(subs) > 1 and _reserve:
+            from irec_b200.native import reserved_sms
+            with reserved_sms(self.RESERVED_SMS):
+                return self.compress_batch(seed, coder, n_streams=len(subs), _again=_again, _reserve=False)
         cur = torch.cuda.current_stream(dev)
         streams = [torch.cuda.Stream(device=dev) for _ in subs] if len(subs) > 1 else [cur]
         fork = torch.cuda.Event()
@@ -140,7 +152,7 @@ class LatentHierarchy:
             if not _again:
                 raise RuntimeError("compress_batch: index-row capacity still too small on the second pass")
             torch.cuda.synchronize(dev)
-            return self.compress_batch(seed, coder, n_streams=n_streams, _again=False)
+            return self.compress_batch(seed, coder, n_streams=n_streams, _again=False, _reserve=_reserve)
         latents = []
         for level in range(n_levels):
             parts = [st["latents"][level] for st in state]
