@@ -599,6 +599,26 @@ def test_exponent_table_cache_across_streams(cuda):
             assert torch.equal(gs, rs), f"launch {i} of repetition {rep}: sample differs"
 
 
+def test_reserved_sms_do_not_change_results(cuda):
+    """irec_set_thread_reserved_sms: the persistent batch kernel runs on fewer SMs (any k, clamped to leave one CTA); same
+    indices and sample bits"""
+    import torch
+    from irec_b200 import Normal
+    from irec_b200.native import reserved_sms
+    from rec.coding import BeamSearchCoder
+    coder = BeamSearchCoder(kl_per_partition=3., n_beams=20, extra_samples=1.2, block_size=1000)
+    arrs = [synth.c2(8192, data_seed=800 + i) for i in range(40)]                   # 360 coder-blocks: the tensor-memory kernel
+    t = Normal(np.stack([a[0] for a in arrs]), np.stack([a[1] for a in arrs]), device=cuda)
+    p = Normal(np.stack([a[2] for a in arrs]), np.stack([a[3] for a in arrs]), device=cuda)
+    ref_idx, ref_sample = coder.encode_batch(t, p, seed=42)
+    for k in (4, 100, 10 ** 6):
+        with reserved_sms(k):
+            idx, sample = coder.encode_batch(t, p, seed=42)
+        assert idx == ref_idx and torch.equal(sample, ref_sample), k
+    idx, sample = coder.encode_batch(t, p, seed=42)                                # setting cleared on exit
+    assert idx == ref_idx and torch.equal(sample, ref_sample)
+
+
 # ------------------------------------------------------------------------------------------ round 2: decode validation, IS candidate table
 def test_decode_rejects_index_lists_beyond_the_ratio_table(cuda):
     """a learned ratio table shorter than an index list must raise CodingError (reference coder.py:226-231),
