@@ -5,15 +5,18 @@ import torch
 
 class Normal:
     """Diagonal Gaussian holder.  `loc` and `scale` are torch tensors of identical shape
-    (anything array-like is converted); no sampling / log_prob is implemented on purpose --
+    (anything array-like or any `__dlpack__` producer is converted); no sampling / log_prob is implemented on purpose --
     that arithmetic lives in the CUDA kernels."""
 
     def __init__(self, loc, scale, device=None):
         def conv(x):
             if not isinstance(x, torch.Tensor):
-                if hasattr(x, "numpy"):
-                    x = x.numpy()
-                x = torch.as_tensor(x)
+                if hasattr(x, "__dlpack__") and hasattr(x, "__dlpack_device__"):
+                    x = torch.from_dlpack(x)       # any DLPack producer, zero-copy (SURVEY.md 8b: data types)
+                else:
+                    if hasattr(x, "numpy"):
+                        x = x.numpy()
+                    x = torch.as_tensor(x)
             x = x.to(dtype=torch.float32)
             if device is not None:
                 x = x.to(device)

@@ -21,9 +21,12 @@ def _f32c(t, device):
     if str(device).startswith("cuda") and not torch.cuda.is_available():
         raise N.NativeError("no CUDA device: the iREC coders run on B200 (sm_100a) only; there is no CPU fallback")
     if not isinstance(t, torch.Tensor):
-        if hasattr(t, "numpy"):
-            t = t.numpy()
-        t = torch.as_tensor(t)
+        if hasattr(t, "__dlpack__") and hasattr(t, "__dlpack_device__"):
+            t = torch.from_dlpack(t)               # zero-copy for CUDA producers (tf eager / cupy / jax arrays)
+        else:
+            if hasattr(t, "numpy"):
+                t = t.numpy()
+            t = torch.as_tensor(t)
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 

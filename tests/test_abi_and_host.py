@@ -103,3 +103,29 @@ def test_product_does_not_import_oracle():
                 for line in open(os.path.join(dp, f)).read().splitlines():
                     low = line.lower()
                     assert not (("import" in low or "include" in low or "cdll" in low) and "oracle" in low), (f, line)
+
+
+def test_distributions_accept_dlpack_producers(built):
+    """SURVEY.md 8b (data types): distributions are duck-typed (.loc / .scale); values may be torch tensors, array-likes or
+    any `__dlpack__` producer (a tf eager tensor, a cupy / jax array) -- taken over without a copy through DLPack"""
+    import numpy as np
+    import torch
+    from irec_b200 import Normal
+
+    class Producer:                                   # only the DLPack protocol, nothing else
+        def __init__(self, a):
+            self._a = a
+
+        def __dlpack__(self, **kw):
+            return self._a.__dlpack__(**kw)
+
+        def __dlpack_device__(self):
+            return self._a.__dlpack_device__()
+
+    loc = np.arange(12, dtype=np.float32).reshape(1, 12)
+    scale = np.full((1, 12), 0.5, np.float32)
+    d = Normal(Producer(loc), Producer(scale))
+    assert isinstance(d.loc, torch.Tensor) and d.loc.dtype == torch.float32
+    assert np.array_equal(d.loc.numpy(), loc) and np.array_equal(d.scale.numpy(), scale)
+    loc[0, 0] = 7.0                                   # zero-copy: the holder sees the producer's memory
+    assert float(d.loc[0, 0]) == 7.0
