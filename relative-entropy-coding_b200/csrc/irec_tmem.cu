@@ -355,35 +355,70 @@ __global__ void __launch_bounds__(256) k_tm_kl_status(const float* __restrict__ 
 }
 
 // Queue order: longest coder-blocks first (work ~ auxiliary variables x 32-dim chunks), so that the blocks handed out last --
-// the ones that decide when the launch ends -- are the short ones.  Counting sort into TM_ORDER_BUCKETS work classes (single CTA).
-#define TM_ORDER_BUCKETS 2048
-__global__ void __launch_bounds__(1024) k_tm_order(const int64_t* __restrict__ offs, const int32_t* __restrict__ n_aux,
-                                                   const int32_t* __restrict__ status, int nb, int32_t* __restrict__ order)
+// the ones that decide when the launch ends -- are the short ones; but only in TM_ORDER_CLASSES coarse work classes, and in
+// the caller's order inside a class (stable counting sort, single CTA).  The caller's order keeps the coder-blocks of one
+// tensor together: Coder.split scatters a tensor's dims over its blocks, so every block touches most 32-byte sectors of the
+// tensor's four parameter arrays and of its sample; coded at about the same time by neighbouring CTAs they share those sectors
+// in L2, coded far apart (the former order by exact work) every block fetched them from DRAM again -- 1.0 GB read per
+// configs[3]-size launch against 0.17 GB algorithmic (profiles/r2_tmem_f_ncu.md).
+#define TM_ORDER_CLASSES 8
+#define TM_ORDER_THREADS 512
+__global__ void __launch_bounds__(TM_ORDER_THREADS) k_tm_order(const int64_t* __restrict__ offs, const int32_t* __restrict__ n_aux,
+                                                               const int32_t* __restrict__ status, int nb, int32_t* __restrict__ order)
 {
-    __shared__ int s_cnt[TM_ORDER_BUCKETS];
+    __shared__ int s_cnt[TM_ORDER_CLASSES][TM_ORDER_THREADS];     // blocks of class c in thread t's contiguous chunk -> start position
     __shared__ int s_max;
     auto work = [&](int b) {
         if (status[b] != IREC_BLK_OK) return 0;
         const int64_t D = offs[b + 1] - offs[b];
         return (int)min((int64_t)0x3fffff, (int64_t)n_aux[b] * ((D + 31) >> 5));
     };
-    for (int i = threadIdx.x; i < TM_ORDER_BUCKETS; i += blockDim.x) s_cnt[i] = 0;
-    if (threadIdx.x == 0) s_max = 1;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_max = 1;
     __syncthreads();
     int mx = 1;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) mx = max(mx, work(b));
+    for (int b = tid; b < nb; b += TM_ORDER_THREADS) mx = max(mx, work(b));
     atomicMax(&s_max, mx);
     __syncthreads();
     const int wmax = s_max;
-    auto bucket = [&](int w) { return (TM_ORDER_BUCKETS - 1) - (int)(((int64_t)w * (TM_ORDER_BUCKETS - 1)) / wmax); };   // 0 = most work
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) atomicAdd(&s_cnt[bucket(work(b))], 1);
+    auto cls = [&](int w) { return (TM_ORDER_CLASSES - 1) - (int)(((int64_t)w * (TM_ORDER_CLASSES - 1)) / wmax); };   // 0 = most work
+    const int per = (nb + TM_ORDER_THREADS - 1) / TM_ORDER_THREADS;
+    const int b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
+    int mine[TM_ORDER_CLASSES];
+#pragma unroll
+    for (int c = 0; c < TM_ORDER_CLASSES; ++c) mine[c] = 0;
+    for (int b = b0; b < b1; ++b) {
+        const int c = cls(work(b));
+#pragma unroll
+        for (int k = 0; k < TM_ORDER_CLASSES; ++k) mine[k] += (k == c);
+    }
+#pragma unroll
+    for (int c = 0; c < TM_ORDER_CLASSES; ++c) s_cnt[c][tid] = mine[c];
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid < TM_ORDER_CLASSES) {                  // per class: exclusive prefix over the threads (chunks in block order)
         int run = 0;
-        for (int i = 0; i < TM_ORDER_BUCKETS; ++i) { const int cnt = s_cnt[i]; s_cnt[i] = run; run += cnt; }   // exclusive prefix
+        for (int t = 0; t < TM_ORDER_THREADS; ++t) { const int v = s_cnt[tid][t]; s_cnt[tid][t] = run; run += v; }
+        mine[0] = run;                             // class total, parked in a register of thread `tid`
+    }
+    __shared__ int s_base[TM_ORDER_CLASSES + 1];
+    if (tid < TM_ORDER_CLASSES) s_base[tid + 1] = mine[0];
+    __syncthreads();
+    if (tid == 0) {
+        s_base[0] = 0;
+        for (int c = 0; c < TM_ORDER_CLASSES; ++c) s_base[c + 1] += s_base[c];
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) order[atomicAdd(&s_cnt[bucket(work(b))], 1)] = b;
+    int pos[TM_ORDER_CLASSES];
+#pragma unroll
+    for (int c = 0; c < TM_ORDER_CLASSES; ++c) pos[c] = s_base[c] + s_cnt[c][tid];
+    for (int b = b0; b < b1; ++b) {
+        const int c = cls(work(b));
+        int p = 0;
+#pragma unroll
+        for (int k = 0; k < TM_ORDER_CLASSES; ++k)
+            if (k == c) { p = pos[k]; pos[k] = p + 1; }
+        order[p] = b;
+    }
 }
 
 template <int BMAX>
@@ -840,7 +875,7 @@ int irec_launch_tmem(const TmemPlan& p, const float* t_loc, const float* t_scale
                                                                            a.ratio_len, out_n_aux, out_status);
     irec_count_launch();
     if (order) {
-        k_tm_order<<<1, 1024, 0, s>>>(offs, out_n_aux, out_status, nb, const_cast<int32_t*>(order));
+        k_tm_order<<<1, TM_ORDER_THREADS, 0, s>>>(offs, out_n_aux, out_status, nb, const_cast<int32_t*>(order));
         irec_count_launch();
     }
     a.prof = nullptr;
