@@ -1329,10 +1329,10 @@ static R2TabCache g_tab_cache[64];
 
 struct R2TabUse { uint2* tab; int tab_aux; R2TabKey* key; R2TabCache* cache; uint2* priv; int allow_rekey; };
 
-// Keep the shared exponent table resident in L2 (persisting access-policy window on the launching stream).  At configs[3] size
-// a launch streams 200 MB of inputs past a 126 MB L2 while every coder-block re-reads its ~7 MB of table rows from L2 (68 GB per
-// launch): without the window ~1.2 % of those reads miss and the table is fetched from DRAM some 50 times per launch
-// (profiles/r2_tmem_f_ncu.md: 1.0 GB read against 0.17 GB algorithmic).  IREC_R2_NO_L2_WINDOW=1 switches it off.
+// Optional (IREC_R2_L2_WINDOW=1): keep the shared exponent table resident in L2 through a persisting access-policy window on the
+// launching stream.  Built to test whether the 1.0 GB of DRAM reads per configs[3]-size launch were table misses -- they were not
+// (966 MB with the window; the cause was the queue order, k_tm_order) -- and OFF by default: the 64 MB set-aside is taken from every
+// other user of L2 (the importance sampler streams a 38 MB candidate table).
 static void r2_tab_l2_window(cudaStream_t s, const void* ptr, size_t bytes)
 {
     static int state[64] = { 0 };                  // per device: 0 = not tried, 1 = on, -1 = unavailable / off
@@ -1341,9 +1341,9 @@ static void r2_tab_l2_window(cudaStream_t s, const void* ptr, size_t bytes)
     if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return;
     if (state[d] == 0) {
         state[d] = -1;
-        const char* e = getenv("IREC_R2_NO_L2_WINDOW");
+        const char* e = getenv("IREC_R2_L2_WINDOW");
         cudaDeviceProp prop;
-        if (!(e && e[0] == '1') && cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+        if ((e && e[0] == '1') && cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
             prop.accessPolicyMaxWindowSize > 0) {
             const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);
             if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
