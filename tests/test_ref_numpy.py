@@ -13,7 +13,9 @@ from oracle import ref_numpy as R
 
 @pytest.mark.parametrize("recipe,D,B,S,omega,seed", [("c1", 64, 1, 36, 3., 42), ("c1", 64, 20, 36, 3., 42),
                                                      ("c2", 192, 20, 36, 3., 42), ("c3", 288, 10, 20, 3., 7),
-                                                     ("c2", 1000, 20, 36, 3., 42)])
+                                                     ("c2", 1000, 20, 36, 3., 42),
+                                                     ("c1", 64, 48, 36, 3., 42),       # n_beams > 32: the wide-beam kernel's range
+                                                     ("c2", 100, 300, 7, 2., 5)])      # S < B: beams grow 1 -> 7 -> 49 -> 300
 def test_numpy_port_agrees_with_oracle(recipe, D, B, S, omega, seed):
     tl, ts, pl, ps = getattr(synth, recipe)(D, data_seed=11)
     ref = O.beam_encode_block(tl, ts, pl, ps, omega, S, B, seed, trace=True)
