@@ -93,7 +93,8 @@ class LatentHierarchy:
         k = max(1, min(int(n_streams), n_images))
         return [(i * n_images // k, (i + 1) * n_images // k) for i in range(k)]
 
-    def compress_batch(self, seed, coder, n_streams=None, _again=True, _reserve=True):
+    def compress_batch(self, seed, coder, n_streams=None, file_paths=None, image_shape=(32, 32, 3), max_index=None,
+                       _again=True, _reserve=True):
         """every image of a batched ladder (`ladder.n_images`; `ladder.prior(level, latents, lo, hi)` with loc/scale of shape
         [hi - lo, ...]) through all levels: what looping `compress` over the images computes, as ONE launch per level and
         sub-batch (`coder.encode_batch(lazy=True)`).  The levels of an image are sequential (its next prior needs its latent),
@@ -108,7 +109,8 @@ class LatentHierarchy:
         if len(subs) > 1 and _reserve:
             from irec_b200.native import reserved_sms
             with reserved_sms(self.RESERVED_SMS):
-                return self.compress_batch(seed, coder, n_streams=len(subs), _again=_again, _reserve=False)
+                return self.compress_batch(seed, coder, n_streams=len(subs), file_paths=file_paths, image_shape=image_shape,
+                                           max_index=max_index, _again=_again, _reserve=False)
         cur = torch.cuda.current_stream(dev)
         streams = [torch.cuda.Stream(device=dev) for _ in subs] if len(subs) > 1 else [cur]
         fork = torch.cuda.Event()
@@ -152,18 +154,36 @@ class LatentHierarchy:
             if not _again:
                 raise RuntimeError("compress_batch: index-row capacity still too small on the second pass")
             torch.cuda.synchronize(dev)
-            return self.compress_batch(seed, coder, n_streams=n_streams, _again=False, _reserve=_reserve)
+            return self.compress_batch(seed, coder, n_streams=n_streams, file_paths=file_paths, image_shape=image_shape,
+                                       max_index=max_index, _again=False, _reserve=_reserve)
         latents = []
         for level in range(n_levels):
             parts = [st["latents"][level] for st in state]
             for t in parts:
                 t.record_stream(cur)
             latents.append(torch.cat(parts, dim=0) if len(parts) > 1 else parts[0])
+        if file_paths is not None:                 # one `.rec` file per image (rec/io/utils.py:7-106), as `compress` writes it
+            if len(file_paths) != n_images:
+                raise ValueError("compress_batch: one file path per image")
+            if max_index is None:
+                max_index = int(getattr(coder, "n_samples", 0)) or (1 + max(i for img in block_indices for t in img for b in t for i in b))
+            for path, per_image in zip(file_paths, block_indices):
+                write_compressed_code(file_path=path, seed=seed, image_shape=tuple(image_shape), block_size=coder.block_size or 0,
+                                      block_indices=per_image, max_index=max_index)
         return block_indices, latents
 
-    def decompress_batch(self, coder, block_indices, seed):
-        """replays the batched ladder from the index lists of `compress_batch`; returns latents[level] of shape [n_images, ...]"""
+    def decompress_batch(self, coder, block_indices=None, seed=None, file_paths=None):
+        """replays the batched ladder from the index lists of `compress_batch` (or from its `.rec` files, one per image);
+        returns latents[level] of shape [n_images, ...]"""
         n_images = self.ladder.n_images
+        if file_paths is not None:
+            block_indices = []
+            for path in file_paths:
+                seed_i, _, _, per_image = read_compressed_code(file_path=path)
+                if seed is not None and seed_i != seed:
+                    raise ValueError("decompress_batch: the files were coded with different seeds")
+                seed = seed_i
+                block_indices.append(per_image)
         latents = []
         for level in range(self.ladder.n_levels):
             prior = self.ladder.prior(level, latents, 0, n_images)

@@ -119,7 +119,7 @@ def test_pipelined_compress_equals_level_by_level(cuda, tmp_path):
 
 
 @pytest.mark.parametrize("block_size", [1000, None])
-def test_compress_batch_equals_per_image(cuda, block_size):
+def test_compress_batch_equals_per_image(cuda, block_size, tmp_path):
     """BASELINE configs[3] as a pipeline with real level-to-level dependence: LatentHierarchy.compress_batch (one launch per
     level and sub-batch, sub-batches on their own CUDA streams, no host synchronisation between levels) == looping `compress`
     over the images, whatever the number of streams; decompress_batch replays it bit for bit"""
@@ -146,3 +146,12 @@ def test_compress_batch_equals_per_image(cuda, block_size):
     dec = batched.decompress_batch(coder, idx, seed=42)
     for level in range(len(shapes)):
         assert torch.equal(dec[level], lat[level])
+    # one .rec file per image, byte-identical to what the per-image loop writes; decode from the files
+    paths = [str(tmp_path / f"img{i}.rec") for i in range(n_images)]
+    batched.compress_batch(seed=42, coder=coder, file_paths=paths)
+    single0 = LatentHierarchy(SyntheticLadder(shapes, recipe="c2", data_seed=40, device=cuda))
+    single0.compress(seed=42, coder=coder, file_path=str(tmp_path / "single0.rec"))
+    assert open(paths[0], "rb").read() == open(str(tmp_path / "single0.rec"), "rb").read()
+    dec_f = batched.decompress_batch(coder, file_paths=paths)
+    for level in range(len(shapes)):
+        assert torch.equal(dec_f[level], lat[level])
