@@ -163,12 +163,20 @@ class BidirectionalResidualBlock(nn.Module):
             elif encoder_args is not None:                                   # compression (:459-470)
                 args = dict(encoder_args)
                 max_aux = args.pop("max_aux", None)
-                if max_aux is not None and hasattr(self.coder, "encode_lazy"):
+                if post_loc.shape[0] > 1:
+                    # a batch of images (extension, BASELINE.json configs[3]): every image coded independently with the same
+                    # seed, ONE launch for the level; `indices` is a callable -> [image][coder_block] lists
+                    if not hasattr(self.coder, "encode_batch"):
+                        raise ModelError("compress_batch needs a coder with encode_batch (beam_search)")
+                    indices, latent_nhwc = self.coder.encode_batch(self.posterior, self.prior, seed=args["seed"], lazy=True)
+                elif max_aux is not None and hasattr(self.coder, "encode_lazy"):
                     # no host synchronisation: `indices` is a callable that reads the lists back later
                     indices, latent_nhwc = self.coder.encode_lazy(self.posterior, self.prior, seed=args["seed"], max_aux=max_aux)
                 else:
                     indices, latent_nhwc = self.coder.encode(self.posterior, self.prior, **args)
                 latent = _nchw(latent_nhwc)
+            elif prior_loc.shape[0] > 1:                                     # decompression of a batch (extension)
+                latent = _nchw(self.coder.decode_batch(self.prior, decoder_args["indices"], seed=decoder_args["seed"]))
             else:                                                            # decompression (:475-476)
                 latent = _nchw(self.coder.decode(self.prior, **decoder_args))
             tensor = self.gen_conv1(tensor)
@@ -240,7 +248,7 @@ class BidirectionalResNetVAE(nn.Module):
 
     # -- :803-836 -------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def compress(self, image, seed, update_sampler=False, max_aux=None):
+    def compress(self, image, seed, update_sampler=False, max_aux=None, _again_done=False):
         """max_aux (extension): promise that no coder-block needs more auxiliary variables than this; the blocks are
         then coded without a host synchronisation between them (BeamSearchCoder.encode_lazy) and the index lists are
         read back after the last block; CodingError if the promise is broken."""
@@ -257,10 +265,39 @@ class BidirectionalResNetVAE(nn.Module):
         for blk in self.residual_blocks:
             indices, t = blk(t, inference_pass=False, encoder_args=enc_args)
             block_indices.append(indices)
-        block_indices = [ind() if callable(ind) else ind for ind in block_indices]
+        pending = block_indices
+        block_indices = [ind() if callable(ind) else ind for ind in pending]
+        if any(getattr(ind, "retried", False) for ind in pending) and not _again_done:
+            # a batched launch ran out of index rows and was repeated after later blocks had consumed its latent: the row
+            # capacity hint has grown, one more pass runs without repeats (engine.PendingBeamResult)
+            return self.compress(image, seed, update_sampler=update_sampler, max_aux=max_aux, _again_done=True)
         rec = self._reconstruct(t)
         self.log_likelihood = self._likelihood(x, rec).mean()
         return block_indices, _nhwc(rec)
+
+    @torch.no_grad()
+    def compress_batch(self, images, seed):
+        """BASELINE.json configs[3]: a batch of images [N, H, W, 3] through the model, every image coded independently (what
+        looping `compress` over them computes, up to the convolutions' batch-size dependent rounding): one coder launch per
+        residual block for the whole batch, no host synchronisation between the blocks, index lists read back at the end.
+        Returns (block_indices[image][res_block][coder_block], reconstructions [N, H, W, 3])."""
+        per_level, rec = self.compress(images, seed)
+        n = images.shape[0]
+        if n == 1:
+            return [per_level], rec
+        return [[per_level[k][i] for k in range(len(per_level))] for i in range(n)], rec
+
+    @torch.no_grad()
+    def decompress_batch(self, compressed_codes, seed, height=32, width=32):
+        """compressed_codes[image][res_block][coder_block] as returned by compress_batch -> images [N, H, W, 3] in [0, 1]"""
+        n = len(compressed_codes)
+        if n == 1:
+            return self.decompress(compressed_codes[0], seed, height=height, width=width)
+        t = self.generative_base(n, height, width)
+        for k, blk in enumerate(self.residual_blocks):
+            codes = [[list(b) for b in compressed_codes[i][k]] for i in range(n)]
+            t = blk(t, inference_pass=False, decoder_args={"seed": seed, "indices": codes})
+        return _nhwc(self._reconstruct(t)) + 0.5
 
     # -- :838-842 -------------------------------------------------------------------------------------------------------
     def get_codelength(self, compressed_codes):

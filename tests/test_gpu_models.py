@@ -54,6 +54,27 @@ def test_rvae_compress_decompress(cuda, num_res_blocks):
     assert lazy_indices == block_indices and torch.equal(lazy_reconstruction, reconstruction)
 
 
+def test_rvae_compress_batch(cuda):
+    """BASELINE.json configs[3] with the real (random-init) networks: a batch of images, one coder launch per residual block;
+    decompress_batch rebuilds the batch from the index lists; every image's code has the shape `compress` gives"""
+    import torch
+    from rec.models import BidirectionalResNetVAE
+    torch.manual_seed(0)
+    model = BidirectionalResNetVAE(num_res_blocks=6, sampler="beam_search", sampler_args={"n_beams": 20, "extra_samples": 1.2},
+                                   coder_args={"block_size": 1000}, deterministic_filters=64, stochastic_filters=32,
+                                   kl_per_partition=3.).to(cuda)
+    images = torch.rand(5, 32, 32, 3, device=cuda) - 0.5
+    model(images)
+    model(images)
+    codes, reconstruction = model.compress_batch(images, seed=42)
+    assert len(codes) == 5 and all(len(img) == 6 and all(len(level) == 9 for level in img) for img in codes)
+    assert all(isinstance(i, int) and 0 <= i < 36 for img in codes for level in img for blk in level for i in blk)
+    assert len({tuple(tuple(b) for level in img for b in level) for img in codes}) == 5          # different images, different codes
+    decoded = model.decompress_batch(codes, seed=42, height=32, width=32)
+    assert decoded.shape == (5, 32, 32, 3)
+    assert torch.allclose(decoded, reconstruction + 0.5, atol=1e-4)
+
+
 def test_rvae_importance_sampler(cuda):
     """`sampler="importance"` builds GaussianCoder(ImportanceSampler) (resnet_vae.py:127-133)"""
     import torch
