@@ -1,3 +1,5 @@
+# HISTORICAL (round 2): IREC_GP_VARIANT selected compile-time variants of k_gp_fused<20> for this A/B only; variant 1 (no in-place
+# bank assignment) is now the only build and the variable is ignored.
 # A/B of the scoring variants of k_gp_fused<20> (IREC_GP_VARIANT, experiment) + one full ncu capture of the default
 mkdir -p gpurun_out
 for v in 0 1 2 3; do

@@ -1,3 +1,5 @@
+# HISTORICAL (round 2): at the time of this run the persisting-L2 window was on by default and IREC_R2_NO_L2_WINDOW=1 switched it off;
+# it is now opt-in (IREC_R2_L2_WINDOW=1).
 # A/B of the persisting-L2 window on the exponent table: DRAM bytes of one configs[3]-size launch (bench value: identical, 3.046e9)
 mkdir -p gpurun_out
 for off in 1 0; do

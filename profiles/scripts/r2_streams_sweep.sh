@@ -1,3 +1,5 @@
+# HISTORICAL (round 2): run when the cross-stream wait on the exponent table was still unconditional; IREC_R2_XSTREAM_EXPERIMENT
+# skipped it for this measurement only.  The library now shares the table across streams safely (r2_tab_acquire) and ignores the variable.
 set -x
 mkdir -p gpurun_out
 export IREC_R2_XSTREAM_EXPERIMENT=1
