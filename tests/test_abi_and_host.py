@@ -129,3 +129,13 @@ def test_distributions_accept_dlpack_producers(built):
     assert np.array_equal(d.loc.numpy(), loc) and np.array_equal(d.scale.numpy(), scale)
     loc[0, 0] = 7.0                                   # zero-copy: the holder sees the producer's memory
     assert float(d.loc[0, 0]) == 7.0
+
+
+def test_reserved_sms_setting_is_host_only(built):
+    """irec_set_thread_reserved_sms is a per-thread host setting (no device call): usable before any CUDA context exists"""
+    from irec_b200 import native as N
+    lib = N.load_library()
+    assert lib.irec_set_thread_reserved_sms(4) == 0
+    assert lib.irec_set_thread_reserved_sms(-1) == 0
+    with N.reserved_sms(8):
+        pass
